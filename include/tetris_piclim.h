@@ -1,0 +1,177 @@
+/* tetris_piclim.h -- C ABI of the B200-native Tetris-piclim rollout hot path (libtetris_piclim_sm100.so).
+ *
+ * Drop-in boundary for the hot path of the reference's game/tetris.py (all file:line citations are
+ * relative to the reference tree): prescribed reset (:438-449), Tetris.move (:354-422) with
+ * calculate_drop(_deltas) (:424-433) and get_tetromino (:60-61), Tetris.get_state (:435-436), plus the
+ * afterstate enumeration + features and the counter-based 7-bag piece RNG the north star adds
+ * (RandomPieceGenerator contract, :64-108).  Plain pointers and sizes only; no torch types.
+ *
+ * Two groups of entry points:
+ *   tpl_*        device-pointer API: every array argument is a DEVICE pointer, work is queued
+ *                asynchronously on `stream` (a cudaStream_t passed as void*); the library never
+ *                allocates, frees or synchronises.
+ *   tpl_env_*    host-buffer API: an opaque handle owns the device state, pinned staging and a
+ *                stream; every array argument is a HOST pointer and the call returns when the
+ *                outputs are valid.  This is what a ctypes binding in the reference would call
+ *                (see INTEGRATION.md).
+ *
+ * All functions return 0 on success, a positive cudaError_t value for CUDA failures, or a negative
+ * TPL_E* code for argument errors; tpl_last_error() returns a thread-local description.
+ *
+ * ---- data formats --------------------------------------------------------------------------------
+ * Canonical (boundary) board: 20 x uint16 bitrows, bit c = column c, row 0 = top (reference board[0]),
+ *   full row = 0x3FF.  Pieces: one byte each, 0=I 1=L 2=J 3=T 4=S 5=Z 6=O (:8-16, :23-57).
+ * Env record (device, 64 bytes = 4 x 16-byte chunks), as 16 little-endian uint32 words:
+ *   w[0..9]   board as 10 bit-columns: bit b of w[c] = cell (row 19-b, column c); bit 0 = floor row
+ *   w[10..13] piece queue, 3 bits per piece, piece i at bits [3i, 3i+3) of the 128-bit value (<= 42 pieces)
+ *   w[14]     lines_cleared (low 16 bits) | moves_used (high 16 bits)
+ *   w[15]     state (byte 0: 0 running / 1 won / 2 lost  == reference None / True / False)
+ *             | head (byte 1: pieces already popped) | npieces (byte 2)
+ * State array ("planes"): chunk j of env i lives at ((uint4*)state)[j * plane_stride + i]; a warp reading
+ *   chunk j of 32 consecutive envs reads 512 contiguous bytes.  Allocate 64 * plane_stride bytes.
+ * Config pool: K records, array-of-structs: record k at ((uint4*)pool)[4*k .. 4*k+3].
+ * Afterstate outputs, slot s = rot*10 + loc (rot 0..3, loc 0..9), slot-major so that stores coalesce:
+ *   feats  uint8[40][n][4] = (rows cleared, holes, bumpiness, aggregate height)
+ *   flags  uint8[40][n]    = TPL_FLAG_* bits
+ *   feats_f32 float[40][n][4] (optional) = the same four numbers as floats (value-net input rows)
+ */
+#ifndef TETRIS_PICLIM_H_
+#define TETRIS_PICLIM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPL_ABI_VERSION 1
+#define TPL_MAX_PIECES 42
+#define TPL_RECORD_BYTES 64
+
+/* move / afterstate flags */
+#define TPL_FLAG_TOPOUT 1    /* drop row < 0: piece consumed, board and moves_used unchanged, state lost (:372-374) */
+#define TPL_FLAG_WIN 2       /* lines_cleared >= L on this clearing move (:415-417) */
+#define TPL_FLAG_LOSE 4      /* moves_used >= M and no win on this move (:389-391, :420-422) */
+#define TPL_FLAG_ALIAS 8     /* afterstates only: (rot, loc) wraps/clamps onto an earlier slot (:61, :364) */
+#define TPL_FLAG_NOPIECE 16  /* piece queue empty: nothing done (the reference raises IndexError at :356) */
+
+/* states */
+#define TPL_RUNNING 0
+#define TPL_WON 1
+#define TPL_LOST 2
+
+/* reset modes */
+#define TPL_RESET_ALL 0      /* every env */
+#define TPL_RESET_MASK 1     /* envs with mask[i] != 0 */
+#define TPL_RESET_DONE 2     /* envs whose state != running or whose queue is empty (auto-reset) */
+
+/* argument errors */
+#define TPL_EINVAL (-1)
+#define TPL_ERANGE (-2)
+#define TPL_ENOMEM (-3)
+
+int tpl_abi_version(void);
+const char *tpl_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * device-pointer API
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Install canonical (rows, pieces) data into records.  Replaces the reset-point hand-over at
+ * game/tetris.py:447 (`self.board, self.pieces = self.queue.get()`) with ctor-fresh counters (:149-151).
+ *   rows u16[n][20]; pieces u8[n][pieces_stride]; npieces u8[n] (each <= 42)
+ *   lines/moves i32[n], st i8[n], head u8[n]: optional (NULL = 0) -- lets tests install mid-episode states
+ *   aos != 0: write a config pool (record k at out[4k..4k+3]); aos == 0: write state planes. */
+int tpl_pack(void *out, int64_t plane_stride, int aos, int n,
+             const uint16_t *rows, const uint8_t *pieces, int pieces_stride, const uint8_t *npieces,
+             const int32_t *lines, const int32_t *moves, const int8_t *st, const uint8_t *head, void *stream);
+
+/* Tetris.get_state (:435-436) for a batch, plus the raw fields tests compare.  Every output is optional.
+ *   rows u16[n][20]; cur/next u8[n] (255 = none); lines/moves i32[n] (cleared/used, NOT remaining);
+ *   st i8[n]; head/npieces u8[n]; queue u8[n][42] = the full piece list including already-popped ones. */
+int tpl_unpack(const void *state, int64_t plane_stride, int n, uint16_t *rows, uint8_t *cur, uint8_t *next,
+               int32_t *lines, int32_t *moves, int8_t *st, uint8_t *head, uint8_t *npieces, uint8_t *queue,
+               void *stream);
+
+/* Tetris.reset + load_warm_reset (:438-449) for the prescribed-config half: copy pool records into envs and
+ * zero lines/moves/state/head.  idx i32[n] picks the config per env; idx == NULL draws
+ * k = mulhi(philox(seed; env_base+i, episode[i], CONFIG).w0, K).  mode: TPL_RESET_*.  episode u32[n] (optional):
+ * incremented for every env reset in mode TPL_RESET_DONE *before* the draw.  gen_count > 0 replaces the pool's
+ * pieces by gen_count pieces of the counter-based 7-bag stream of (seed, env, episode). */
+int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *pool, int K,
+                        const int32_t *idx, const uint8_t *mask, int mode, uint32_t *episode,
+                        uint64_t seed, uint64_t env_base, int gen_count, void *stream);
+
+/* Tetris.move (:354-422) on every env: rot u8[n] (already reduced mod 4 by the caller; rot % n_rot is applied
+ * here), loc u8[n] (clamped to 10 - width like :364).  Outputs (each optional): dlines i8[n] rows cleared,
+ * flags u8[n] TPL_FLAG_*, st i8[n] state after the move. */
+int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc,
+             int8_t *dlines, uint8_t *flags, int8_t *st, int L, int M, void *stream);
+
+/* Afterstate enumeration: slot (r, c) == clone(env).move(r, c) (composition of :354-422), with features on
+ * the post-move board (the unchanged board when the move tops out).  feats/flags/feats_f32 as described
+ * above; any of the three may be NULL. */
+int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *feats, uint8_t *flags,
+                    float *feats_f32, int L, int M, void *stream);
+
+/* Counter-based 7-bag piece sequences (contract of RandomPieceGenerator.get_random_sequence, :95-102):
+ * out u8[n][count]; episode u32[n] or NULL (= episode0 for all). */
+int tpl_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode,
+                   uint32_t episode0, void *stream);
+
+/* Fused random-agent rollout (config 1's agent: rot ~ U{0..3}, loc ~ U{0..9} from the counter RNG), `steps`
+ * moves per env with auto-reset from the pool, state kept in registers between moves.
+ *   episode/tstep u32[n] in/out; stats i64[8] += {episodes, wins, top-outs, move-limit losses, lines,
+ *   moves placed, steps, resets}. */
+int tpl_rollout_random(void *state, int64_t plane_stride, int n, const void *pool, int K,
+                       uint32_t *episode, uint32_t *tstep, long long *stats, int steps,
+                       uint64_t seed, uint64_t env_base, int gen_count, int L, int M, void *stream);
+
+/* Fused greedy rollout: every step enumerates the 40 afterstates in registers, scores each with the integer
+ * linear value w[0]*dlines + w[1]*holes + w[2]*bumpiness + w[3]*agg_height (+ w[4] if it wins, + w[5] if it loses
+ * or tops out), plays the arg-max slot (lowest slot on ties) and auto-resets.  weights6_host: HOST int32[6].
+ * Same in/out arrays as above. */
+int tpl_rollout_greedy(void *state, int64_t plane_stride, int n, const void *pool, int K,
+                       uint32_t *episode, uint32_t *tstep, long long *stats, int steps, const int32_t *weights6_host,
+                       uint64_t seed, uint64_t env_base, int gen_count, int L, int M, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * host-buffer API (handle owns device memory; every array is a HOST pointer)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tpl_env tpl_env;
+
+/* Tetris.__init__(L, M, ...) (:141-151) for n envs on CUDA device `device`. */
+int tpl_env_create(tpl_env **out, int n, int L, int M, int device, uint64_t seed, uint64_t env_base);
+void tpl_env_destroy(tpl_env *e);
+/* upload K prescribed reset points (the (board, pieces) tuples of :476-479) */
+int tpl_env_set_pool(tpl_env *e, int K, const uint16_t *rows, const uint8_t *pieces, int pieces_stride,
+                     const uint8_t *npieces);
+/* reset (:438-449): idx i32[n] or NULL (counter-RNG draw), mask u8[n] or NULL, mode TPL_RESET_* */
+int tpl_env_reset(tpl_env *e, const int32_t *idx, const uint8_t *mask, int mode, int gen_count);
+/* install explicit states (tests, the single-env facade) */
+int tpl_env_load(tpl_env *e, const uint16_t *rows, const uint8_t *pieces, int pieces_stride, const uint8_t *npieces,
+                 const int32_t *lines, const int32_t *moves, const int8_t *st, const uint8_t *head);
+/* move (:354-422): host rot/loc in, host dlines/flags/st out (outputs optional) */
+int tpl_env_move(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags, int8_t *st);
+/* get_state (:435-436) */
+int tpl_env_get_state(tpl_env *e, uint16_t *rows, uint8_t *cur, uint8_t *next, int32_t *lines, int32_t *moves,
+                      int8_t *st, uint8_t *head, uint8_t *npieces, uint8_t *queue);
+/* afterstates to host: feats u8[40][n][4], flags u8[40][n] */
+int tpl_env_afterstates(tpl_env *e, uint8_t *feats, uint8_t *flags);
+/* one fused host-facing rollout step: H2D actions -> move -> auto-reset of finished envs -> afterstates of the
+ * new states -> D2H (dlines, flags, st, feats, aflags).  This is the call bench.py's e2e figure times. */
+int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
+                         int8_t *st, uint8_t *feats, uint8_t *aflags);
+/* pinned (page-locked) host buffers so the copies inside the calls above are true async DMA */
+void *tpl_host_alloc(int64_t bytes);
+void tpl_host_free(void *p);
+/* raw access for callers that keep data on the device (torch): device pointer of the state planes */
+void *tpl_env_state_ptr(tpl_env *e, int64_t *plane_stride);
+void *tpl_env_stream(tpl_env *e);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+long long tpl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRIS_PICLIM_H_ */

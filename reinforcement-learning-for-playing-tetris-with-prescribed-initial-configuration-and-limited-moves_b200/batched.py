@@ -1,0 +1,269 @@
+"""``BatchedTetris``: N Tetris-piclim envs resident on one B200, driven through the C ABI.
+
+Same verbs as the reference's ``Tetris`` (``game/tetris.py:140``: ``reset`` ``:438``, ``move`` ``:354``,
+``get_state`` ``:435``, ``terminate`` ``:451``) on tensors instead of one board, plus ``afterstates()`` and the
+fused rollouts.  PyTorch is used for device memory and streams only; every computation is a kernel of
+``libtetris_piclim_sm100.so`` queued on torch's current stream.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .configs import MAX_PIECES, ConfigPool
+
+RUNNING, WON, LOST = 0, 1, 2
+FLAG_TOPOUT, FLAG_WIN, FLAG_LOSE, FLAG_ALIAS, FLAG_NOPIECE = 1, 2, 4, 8, 16
+RESET_ALL, RESET_MASK, RESET_DONE = 0, 1, 2
+
+STAT_NAMES = ("episodes", "wins", "topouts", "movelimit_losses", "lines", "moves", "steps", "resets")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BatchedTetris:
+    """N envs with shared (L, M).  ``env_base`` is the global id of env 0 (multi-GPU sharding keeps the RNG
+    streams a function of the *global* env id, so results do not depend on the number of ranks)."""
+
+    def __init__(self, num_envs: int, L: int, M: int, device="cuda", seed: int = 0,
+                 config_pool: Optional[ConfigPool] = None, env_base: int = 0, gen_pieces: int = 0):
+        if num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        if not (0 <= L <= 65535 and 0 <= M <= 65535):
+            raise ValueError("L and M must fit 16 bits")
+        self._L = _lib.lib()                                    # raises if the CUDA library is missing
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedTetris is CUDA-only (B200, sm_100a); there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs, self.L, self.M = int(num_envs), int(L), int(M)
+        self.seed, self.env_base, self.gen_pieces = int(seed), int(env_base), int(gen_pieces)
+        self.stride = (self.num_envs + 31) // 32 * 32
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros((4, self.stride, 4), dtype=torch.int32, device=self.device)
+            self.episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            self.tstep = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            self.stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.pool = None
+        self.pool_size = 0
+        self._out = {}
+        if config_pool is not None:
+            self.set_pool(config_pool)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype, shape=None) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=dtype)
+        else:
+            a = np.ascontiguousarray(x)
+            if dtype == torch.uint16:
+                t = torch.from_numpy(a.astype(np.uint16).view(np.int16)).to(self.device).view(torch.uint16)
+            else:
+                t = torch.as_tensor(a).to(device=self.device, dtype=dtype)
+        t = t.contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def _buf(self, name, shape, dtype) -> torch.Tensor:
+        t = self._out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._out[name] = t
+        return t
+
+    # ------------------------------------------------------------------ config pool / reset (E)
+    def set_pool(self, pool: ConfigPool) -> None:
+        rows = np.ascontiguousarray(pool.rows, np.uint16)
+        K = rows.shape[0]
+        if rows.shape != (K, 20) or K == 0:
+            raise ValueError("pool rows must be uint16[K, 20] with K > 0")
+        pieces = np.ascontiguousarray(pool.pieces, np.uint8)
+        npieces = np.ascontiguousarray(pool.npieces, np.uint8)
+        if pieces.ndim != 2 or pieces.shape[0] != K or npieces.shape != (K,):
+            raise ValueError("pool pieces must be uint8[K, P] and npieces uint8[K]")
+        if int(npieces.max()) > min(MAX_PIECES, pieces.shape[1]) or int(npieces.min()) < 1:
+            raise ValueError("each config needs 1..42 pieces (and no more than the pieces array holds)")
+        if int(pieces.max()) > 6:
+            raise ValueError("piece ids must be 0..6")
+        d_rows, d_p, d_np = self._dev(rows, torch.uint16), self._dev(pieces, torch.uint8), self._dev(npieces, torch.uint8)
+        self.pool = torch.empty((K, 4, 4), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.tpl_pack(_ptr(self.pool), 0, 1, K, _ptr(d_rows), _ptr(d_p), pieces.shape[1], _ptr(d_np),
+                                    None, None, None, None, self._stream()), "tpl_pack(pool)")
+        self.pool_size = K
+
+    def reset(self, mask=None, idx=None, boards=None, pieces=None, npieces=None, done_only: bool = False) -> None:
+        """Prescribed reset (``game/tetris.py:438-449``) with ctor-fresh counters (``:149-151``).
+
+        * ``boards``/``pieces`` given: install exactly these (uint16[N,20] bitrows or bool[N,20,10]; uint8[N,P]).
+        * otherwise draw from the pool: ``idx`` int32[N] picks configs, else the counter RNG keyed by
+          (seed, global env id, episode) does.  ``mask`` restricts the reset to some envs; ``done_only`` resets
+          exactly the envs whose episode has ended and bumps their episode counter (auto-reset)."""
+        n = self.num_envs
+        if boards is not None:
+            if mask is not None or done_only:
+                raise ValueError("explicit boards reset every env")
+            self.load(boards, pieces, npieces)
+            self.episode.zero_(); self.tstep.zero_()
+            return
+        if self.pool is None:
+            raise RuntimeError("reset() needs a config pool (set_pool) or explicit boards")
+        mode = RESET_DONE if done_only else (RESET_MASK if mask is not None else RESET_ALL)
+        d_mask = self._dev(mask, torch.uint8, (n,)) if mask is not None else None
+        d_idx = self._dev(idx, torch.int32, (n,)) if idx is not None else None
+        if mode == RESET_ALL:
+            self.episode.zero_()
+        if mode != RESET_DONE:
+            (self.tstep.zero_() if d_mask is None else self.tstep.masked_fill_(d_mask.bool(), 0))
+        _lib.check(self._L.tpl_reset_from_pool(_ptr(self.state), self.stride, n, _ptr(self.pool), self.pool_size,
+                                               _ptr(d_idx), _ptr(d_mask), mode, _ptr(self.episode), self.seed,
+                                               self.env_base, self.gen_pieces, self._stream()), "tpl_reset_from_pool")
+
+    def load(self, boards, pieces, npieces=None, lines=None, moves=None, state=None, head=None) -> None:
+        """Install explicit env states (boundary format).  Optional counters let tests resume mid-episode."""
+        n = self.num_envs
+        b = boards.detach().cpu().numpy() if isinstance(boards, torch.Tensor) else np.asarray(boards)
+        if b.dtype == bool or b.ndim == 3:
+            from .configs import rows_from_bool
+            b = rows_from_bool(b)
+        d_rows = self._dev(b, torch.uint16, (n, 20))
+        p = pieces.detach().cpu().numpy() if isinstance(pieces, torch.Tensor) else np.asarray(pieces)
+        if p.ndim != 2 or p.shape[0] != n:
+            raise ValueError("pieces must be [N, P]")
+        if npieces is None:
+            npieces = np.full(n, p.shape[1], np.uint8)
+        npn = np.asarray(npieces)
+        if npn.max() > min(MAX_PIECES, p.shape[1]):
+            raise ValueError("npieces exceeds the 42-piece queue or the pieces array")
+        d_p, d_np = self._dev(p, torch.uint8), self._dev(npn, torch.uint8, (n,))
+        opt = lambda x, dt: self._dev(x, dt, (n,)) if x is not None else None   # noqa: E731
+        d_lines, d_moves, d_st, d_head = opt(lines, torch.int32), opt(moves, torch.int32), opt(state, torch.int8), opt(head, torch.uint8)
+        _lib.check(self._L.tpl_pack(_ptr(self.state), self.stride, 0, n, _ptr(d_rows), _ptr(d_p), p.shape[1], _ptr(d_np),
+                                    _ptr(d_lines), _ptr(d_moves), _ptr(d_st), _ptr(d_head), self._stream()), "tpl_pack")
+
+    # ------------------------------------------------------------------ move (C)
+    def move(self, rot, loc) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``Tetris.move(rotations, location)`` (``game/tetris.py:354-422``) on every env.
+
+        ``rot`` may be any integers (reduced with Python's ``%`` like ``:61``); ``loc`` must be >= 0 (a negative
+        location raises in the reference too) and is clamped to ``10 - width`` (``:364``).
+        Returns (rows cleared int8[N], flags uint8[N], state int8[N])."""
+        n = self.num_envs
+        if isinstance(rot, torch.Tensor):
+            r = torch.remainder(rot.to(self.device), 4).to(torch.uint8)
+        else:
+            r = np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8)
+        if isinstance(loc, torch.Tensor):
+            if loc.dtype != torch.uint8 and bool((loc < 0).any()):
+                raise ValueError("location must be >= 0")
+            l = loc.to(self.device).clamp(max=255).to(torch.uint8)
+        else:
+            la = np.asarray(loc, np.int64)
+            if (la < 0).any():
+                raise ValueError("location must be >= 0")
+            l = np.minimum(la, 255).astype(np.uint8)
+        d_rot, d_loc = self._dev(r, torch.uint8, (n,)), self._dev(l, torch.uint8, (n,))
+        dl = self._buf("dlines", (n,), torch.int8)
+        fl = self._buf("mflags", (n,), torch.uint8)
+        st = self._buf("mstate", (n,), torch.int8)
+        _lib.check(self._L.tpl_step(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
+                                    self.L, self.M, self._stream()), "tpl_step")
+        self.tstep += 1
+        return dl, fl, st
+
+    step = move
+
+    # ------------------------------------------------------------------ observation (D)
+    def get_state(self, bool_boards: bool = False):
+        """Batched ``Tetris.get_state`` (``game/tetris.py:435-436``):
+        (boards uint16[N,20] or bool[N,20,10], current piece uint8[N], next piece uint8[N] (255 = none),
+        L - lines_cleared int32[N], M - moves_used int32[N], state int8[N])."""
+        f = self.fields()
+        boards = f["rows"]
+        if bool_boards:
+            boards = ((boards.to(torch.int32)[..., None] >> torch.arange(10, device=self.device)) & 1).bool()
+        return boards, f["cur"], f["next"], self.L - f["lines"], self.M - f["moves"], f["state"]
+
+    def fields(self, queue: bool = False) -> dict:
+        n = self.num_envs
+        rows = self._buf("rows", (n, 20), torch.uint16)
+        cur, nxt = self._buf("cur", (n,), torch.uint8), self._buf("next", (n,), torch.uint8)
+        lines, moves = self._buf("lines", (n,), torch.int32), self._buf("moves", (n,), torch.int32)
+        st, head, npc = self._buf("state", (n,), torch.int8), self._buf("head", (n,), torch.uint8), self._buf("np", (n,), torch.uint8)
+        q = self._buf("queue", (n, MAX_PIECES), torch.uint8) if queue else None
+        _lib.check(self._L.tpl_unpack(_ptr(self.state), self.stride, n, _ptr(rows), _ptr(cur), _ptr(nxt), _ptr(lines), _ptr(moves),
+                                      _ptr(st), _ptr(head), _ptr(npc), _ptr(q), self._stream()), "tpl_unpack")
+        out = dict(rows=rows, cur=cur, next=nxt, lines=lines, moves=moves, state=st, head=head, npieces=npc)
+        if queue:
+            out["queue"] = q
+        return out
+
+    # ------------------------------------------------------------------ afterstates (F)
+    def afterstates(self, f32: bool = False, u8: bool = True):
+        """All 40 afterstates of every env: slot (r, c) == clone(env).move(r, c).
+
+        Returns (feats, flags[, feats_f32]): ``feats`` uint8 viewed as [N, 4, 10, 4] = (rows cleared, holes,
+        bumpiness, aggregate height), ``flags`` uint8 [N, 4, 10]; both are strided views of slot-major buffers
+        ([40, N, 4] / [40, N]) so no copy is made.  ``feats_f32`` (if requested) is float32 [40*N, 4] in
+        slot-major row order (row s*N + i), ready to be fed to the value net."""
+        n = self.num_envs
+        feats = self._buf("feats", (40, n, 4), torch.uint8) if u8 else None
+        flags = self._buf("aflags", (40, n), torch.uint8)
+        ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
+        _lib.check(self._L.tpl_afterstates(_ptr(self.state), self.stride, n, _ptr(feats), _ptr(flags), _ptr(ff), self.L, self.M,
+                                           self._stream()), "tpl_afterstates")
+        fv = feats.view(4, 10, n, 4).permute(2, 0, 1, 3) if u8 else None
+        gv = flags.view(4, 10, n).permute(2, 0, 1)
+        return (fv, gv, ff) if f32 else (fv, gv)
+
+    # ------------------------------------------------------------------ fused rollouts
+    def _need_pool(self):
+        if self.pool is None:
+            raise RuntimeError("rollouts auto-reset from a config pool: call set_pool first")
+
+    def rollout_random(self, steps: int) -> None:
+        """``steps`` uniformly random moves per env with auto-reset; state stays in registers between moves.
+        Episode statistics accumulate in ``self.stats`` (see STAT_NAMES)."""
+        self._need_pool()
+        _lib.check(self._L.tpl_rollout_random(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
+                                              _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps), self.seed,
+                                              self.env_base, self.gen_pieces, self.L, self.M, self._stream()), "tpl_rollout_random")
+
+    def rollout_greedy(self, steps: int, weights: Sequence[int]) -> None:
+        """``steps`` greedy moves per env: arg-max over the 40 afterstates of the integer linear value
+        w0*dlines + w1*holes + w2*bumpiness + w3*agg_height (+ w4 on a win, + w5 on a loss / top-out)."""
+        self._need_pool()
+        w = (ctypes.c_int32 * 6)(*[int(x) for x in weights])
+        _lib.check(self._L.tpl_rollout_greedy(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
+                                              _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps),
+                                              ctypes.cast(w, ctypes.c_void_p), self.seed, self.env_base, self.gen_pieces,
+                                              self.L, self.M, self._stream()), "tpl_rollout_greedy")
+
+    def gen_pieces(self, count: int, episode: int = 0) -> torch.Tensor:
+        out = torch.empty((self.num_envs, count), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.tpl_gen_pieces(_ptr(out), self.num_envs, count, self.seed, self.env_base, None, episode, self._stream()),
+                   "tpl_gen_pieces")
+        return out
+
+    def reduce_stats(self) -> dict:
+        """Episode statistics, summed over all ranks when torch.distributed is initialised (the one collective
+        of the path: a 64-byte all-reduce per rollout)."""
+        s = self.stats.clone()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        return dict(zip(STAT_NAMES, (int(v) for v in s.tolist())))
+
+    def terminate(self) -> None:
+        """API parity with ``Tetris.terminate`` (``game/tetris.py:451``): there are no worker processes to join."""
+        return None

@@ -1,0 +1,272 @@
+// piclim_core.cuh -- device-side core of the B200 Tetris-piclim hot path (sm_100a).
+//
+// Everything here restates, on a bit-column board, the semantics of the reference's
+// game/tetris.py (citations are file:line in the reference tree):
+//   tetromino table + get_tetromino   :23-57, :60-61
+//   calculate_drop(_deltas)           :424-433
+//   Tetris.move                       :354-422
+// Board representation: 10 x uint32 "bit-columns"; bit b of col[c] is the cell in row (19 - b) of
+// column c, so bit 0 is the floor row and the column height is simply 32 - clz(col[c]).  With the
+// board stored column-wise, every quantity the move needs is one or two integer instructions per
+// column: hard-drop = max over <= 4 columns of (height - piece bottom offset), placement = OR of a
+// shifted 4-bit piece column, full rows = AND over the ten columns, line clear = deleting <= 4 bit
+// positions from each column.  The boundary format (20 x uint16 bitrows, row 0 = top) is converted
+// in tpl_pack / tpl_unpack only.
+#pragma once
+#include <stdint.h>
+#ifdef TPL_HOST_EMUL
+// tests/emul/ compiles this header with g++ to unit-test the device logic on a CPU-only box
+// (test infrastructure; the product library is only ever built by nvcc for sm_100a).
+#include "../../tests/emul/host_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace tpl {
+
+constexpr int ROWS = 20;
+constexpr int COLS = 10;
+constexpr uint32_t COL_FULL = 0xFFFFFu;
+
+enum : uint32_t { F_TOPOUT = 1, F_WIN = 2, F_LOSE = 4, F_ALIAS = 8, F_NOPIECE = 16 };
+enum : uint32_t { S_RUNNING = 0, S_WON = 1, S_LOST = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// A. orientation table.  One uint4 per (piece, rot 0..3); rot >= n_rot repeats rot % n_rot (:61).
+//   x: bits 0-15  cb   : 4-bit column images, nibble j = shape column j, bit i = cell i rows above
+//                        the shape's bottom row
+//      bits 16-18 w, bits 20-22 h, bits 24-25 n_rot-1, bit 28 = rot is an alias (rot >= n_rot)
+//   y: bo bytes: byte j = rows between the shape's bottom row and the lowest cell of column j
+//      (= h-1-profile[j] with profile the tuple at :25-55); 64 for j >= w so it never wins the max
+//   z: to bytes: byte j = (height of the highest cell of column j above the bottom row) + 1
+//   w: bo nibbles (4 bits per column, no sentinel) in bits 0-15 -- used by the column-aligned path
+// ---------------------------------------------------------------------------------------------
+struct OrientEntry { uint32_t x, y, z, w; };
+
+constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool alias) {
+    int m[4] = {m0, m1, m2, m3};
+    int h = 0, w = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (m[i]) h = i + 1;
+        for (int j = 0; j < 4; ++j) if ((m[i] >> j) & 1) { if (j + 1 > w) w = j + 1; }
+    }
+    uint32_t cb = 0, bo = 0, to = 0, bon = 0;
+    for (int j = 0; j < 4; ++j) {
+        if (j >= w) { bo |= 64u << (8 * j); continue; }
+        int lowest = -1, highest = -1;
+        for (int i = 0; i < h; ++i) if ((m[i] >> j) & 1) {
+            lowest = i; if (highest < 0) highest = i;
+            cb |= 1u << (4 * j + (h - 1 - i));
+        }
+        bo |= (uint32_t)(h - 1 - lowest) << (8 * j);
+        bon |= (uint32_t)(h - 1 - lowest) << (4 * j);
+        to |= (uint32_t)(h - highest) << (8 * j);
+    }
+    return OrientEntry{cb | ((uint32_t)w << 16) | ((uint32_t)h << 20) | ((uint32_t)(nrot - 1) << 24) | (alias ? 1u << 28 : 0u),
+                       bo, to, bon};
+}
+
+// row masks top->bottom, bit j = shape column j, exactly the arrays at game/tetris.py:25-55
+#define TPL_O(a, b, c, d, n, al) make_orient(a, b, c, d, n, al)
+__constant__ OrientEntry c_orient[28] = {
+    // I
+    TPL_O(0xF, 0, 0, 0, 2, false), TPL_O(1, 1, 1, 1, 2, false), TPL_O(0xF, 0, 0, 0, 2, true), TPL_O(1, 1, 1, 1, 2, true),
+    // L
+    TPL_O(4, 7, 0, 0, 4, false), TPL_O(3, 2, 2, 0, 4, false), TPL_O(7, 1, 0, 0, 4, false), TPL_O(1, 1, 3, 0, 4, false),
+    // J
+    TPL_O(1, 7, 0, 0, 4, false), TPL_O(2, 2, 3, 0, 4, false), TPL_O(7, 4, 0, 0, 4, false), TPL_O(3, 1, 1, 0, 4, false),
+    // T
+    TPL_O(2, 7, 0, 0, 4, false), TPL_O(2, 3, 2, 0, 4, false), TPL_O(7, 2, 0, 0, 4, false), TPL_O(1, 3, 1, 0, 4, false),
+    // S
+    TPL_O(6, 3, 0, 0, 2, false), TPL_O(1, 3, 2, 0, 2, false), TPL_O(6, 3, 0, 0, 2, true), TPL_O(1, 3, 2, 0, 2, true),
+    // Z
+    TPL_O(3, 6, 0, 0, 2, false), TPL_O(2, 3, 1, 0, 2, false), TPL_O(3, 6, 0, 0, 2, true), TPL_O(2, 3, 1, 0, 2, true),
+    // O
+    TPL_O(3, 3, 0, 0, 1, false), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true),
+};
+#undef TPL_O
+
+__device__ __forceinline__ int orient_w(const uint4 &o) { return (o.x >> 16) & 7; }
+__device__ __forceinline__ int orient_h(const uint4 &o) { return (o.x >> 20) & 7; }
+__device__ __forceinline__ int orient_nrot(const uint4 &o) { return ((o.x >> 24) & 3) + 1; }
+__device__ __forceinline__ bool orient_alias(const uint4 &o) { return (o.x >> 28) & 1; }
+
+// ---------------------------------------------------------------------------------------------
+// env record in registers
+// ---------------------------------------------------------------------------------------------
+struct Env {
+    uint32_t col[COLS];
+    uint32_t q[4];          // piece queue, 3 bits per piece
+    uint32_t lines, moves, state, head, npieces;
+};
+
+__device__ __forceinline__ uint4 ldg_plain(const uint4 *p) { return *p; }
+
+__device__ __forceinline__ void unpack_env(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, Env &e) {
+    e.col[0] = a.x; e.col[1] = a.y; e.col[2] = a.z; e.col[3] = a.w;
+    e.col[4] = b.x; e.col[5] = b.y; e.col[6] = b.z; e.col[7] = b.w;
+    e.col[8] = c.x; e.col[9] = c.y; e.q[0] = c.z; e.q[1] = c.w;
+    e.q[2] = d.x; e.q[3] = d.y;
+    e.lines = d.z & 0xFFFFu; e.moves = d.z >> 16;
+    e.state = d.w & 0xFFu; e.head = (d.w >> 8) & 0xFFu; e.npieces = (d.w >> 16) & 0xFFu;
+}
+__device__ __forceinline__ uint4 pack_meta(const Env &e) {
+    return make_uint4(e.q[2], e.q[3], (e.lines & 0xFFFFu) | (e.moves << 16),
+                      (e.state & 0xFFu) | ((e.head & 0xFFu) << 8) | ((e.npieces & 0xFFu) << 16));
+}
+
+// state planes: chunk j of env i at st[j * stride + i]
+__device__ __forceinline__ void load_env(const uint4 *st, int64_t stride, int64_t i, Env &e) {
+    uint4 a = ldg_plain(st + i), b = ldg_plain(st + stride + i), c = ldg_plain(st + 2 * stride + i),
+          d = ldg_plain(st + 3 * stride + i);
+    unpack_env(a, b, c, d, e);
+}
+__device__ __forceinline__ void store_env(uint4 *st, int64_t stride, int64_t i, const Env &e) {
+    st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+    st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+    st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+    st[3 * stride + i] = pack_meta(e);
+}
+
+// piece `idx` of the 128-bit queue
+__device__ __forceinline__ uint32_t queue_piece(const uint32_t (&q)[4], uint32_t idx) {
+    uint32_t bit = 3u * idx, wd = bit >> 5, off = bit & 31u;
+    uint32_t lo = wd == 0 ? q[0] : wd == 1 ? q[1] : wd == 2 ? q[2] : q[3];
+    uint32_t hi = wd == 0 ? q[1] : wd == 1 ? q[2] : wd == 2 ? q[3] : 0u;
+    return __funnelshift_r(lo, hi, off) & 7u;
+}
+
+__device__ __forceinline__ int col_height(uint32_t c) { return 32 - __clz(c); }
+
+// ---------------------------------------------------------------------------------------------
+// C. the general move on bit-columns (any loc, static column indexing only).
+//    Returns rows cleared (0..4); topout set when drop row < 0 (board untouched, :372-374).
+// ---------------------------------------------------------------------------------------------
+struct MoveOut { int k; bool topout; };
+
+__device__ __forceinline__ MoveOut place_general(uint32_t (&x)[COLS], const uint4 &o, int loc_raw) {
+    const int w = orient_w(o), h = orient_h(o);
+    const int loc = min(loc_raw, COLS - w);                                  // :364
+    // align the piece's 4-bit column images / bottom offsets with the board columns
+    const uint64_t PB = (uint64_t)(o.x & 0xFFFFu) << (4 * loc);
+    const uint64_t BO = (uint64_t)(o.w & 0xFFFFu) << (4 * loc);
+    uint32_t pk[COLS];
+    int y = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        pk[k] = (uint32_t)(PB >> (4 * k)) & 15u;
+        const int bo = (int)((uint32_t)(BO >> (4 * k)) & 15u);
+        const int d = col_height(x[k]) - bo;                                 // :427-433 in height form
+        y = pk[k] ? max(y, d) : y;
+    }
+    MoveOut r; r.k = 0; r.topout = (y + h > ROWS);                            // drop = 20 - h - y < 0
+    if (r.topout) return r;
+    uint32_t full = ((1u << h) - 1u) << y;                                    // only the piece's rows (:382-383)
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { x[k] |= pk[k] << y; full &= x[k]; }      // :377-378
+    r.k = __popc(full);
+    while (full) {                                                            // :397-407, highest row first
+        const int q = 31 - __clz(full);
+        const uint32_t low = (1u << q) - 1u;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) x[k] = (x[k] & low) | ((x[k] >> 1) & ~low);
+        full &= ~(1u << q);
+    }
+    return r;
+}
+
+// win / lose bookkeeping shared by every caller (:379, :389-391, :409-422)
+__device__ __forceinline__ uint32_t apply_outcome(Env &e, const MoveOut &m, int L, int M) {
+    uint32_t fl = 0;
+    if (m.topout) { e.state = S_LOST; return F_TOPOUT; }
+    e.moves += 1;
+    if (m.k == 0) {
+        if ((int)e.moves >= M) { e.state = S_LOST; fl = F_LOSE; }
+        return fl;
+    }
+    e.lines += (uint32_t)m.k;
+    if ((int)e.lines >= L) { e.state = S_WON; fl = F_WIN; }
+    else if ((int)e.moves >= M) { e.state = S_LOST; fl = F_LOSE; }
+    return fl;
+}
+
+// features of a bit-column board: holes | bumpiness<<8 | agg<<16
+__device__ __forceinline__ uint32_t board_features(const uint32_t (&x)[COLS], int cells) {
+    int hprev = col_height(x[0]);
+    int agg = hprev, bump = 0;
+#pragma unroll
+    for (int k = 1; k < COLS; ++k) {
+        const int hk = col_height(x[k]);
+        agg += hk; bump += abs(hk - hprev); hprev = hk;
+    }
+    return (uint32_t)(agg - cells) | ((uint32_t)bump << 8) | ((uint32_t)agg << 16);
+}
+
+__device__ __forceinline__ int board_cells(const uint32_t (&x)[COLS]) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c += __popc(x[k]);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// G. Philox4x32-10 (Salmon et al. SC'11) and the 7-bag built on it
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { STREAM_PIECES = 0, STREAM_ACTION = 1, STREAM_CONFIG = 2 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 rng_words(uint64_t seed, uint64_t env, uint32_t episode, uint32_t stream, uint32_t index) {
+    return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), episode, (stream << 28) | (index & 0x0FFFFFFFu)),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// one uniformly chosen permutation of 0..6 as seven 3-bit fields (field t = t-th piece of the bag)
+__device__ __forceinline__ uint32_t bag_from_word(uint32_t u) {
+    uint32_t k = __umulhi(u, 5040u);
+    uint32_t perm = 0u;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) perm |= (uint32_t)t << (3 * t);
+#pragma unroll
+    for (int i = 6; i >= 1; --i) {
+        const uint32_t j = k % (uint32_t)(i + 1);
+        k /= (uint32_t)(i + 1);
+        const uint32_t x = ((perm >> (3 * i)) ^ (perm >> (3 * j))) & 7u;
+        perm ^= (x << (3 * i)) | (x << (3 * j));
+    }
+    return perm;
+}
+
+// the first `count` (<= 42) pieces of episode `episode` of env `env`, packed 3 bits each
+__device__ __forceinline__ void gen_queue(uint64_t seed, uint64_t env, uint32_t episode, int count, uint32_t (&q)[4]) {
+    uint64_t lo = 0, hi = 0;
+    uint4 w0 = rng_words(seed, env, episode, STREAM_PIECES, 0);
+    uint4 w1 = rng_words(seed, env, episode, STREAM_PIECES, 1);
+    const uint32_t ws[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const uint64_t perm = bag_from_word(ws[b]);
+        const int off = 21 * b;
+        if (off < 64) { lo |= perm << off; if (off + 21 > 64) hi |= perm >> (64 - off); }
+        else hi |= perm << (off - 64);
+    }
+    const int bits = 3 * count;
+    if (bits < 64) { lo &= (1ull << bits) - 1ull; hi = 0; }
+    else if (bits < 128) hi &= (1ull << (bits - 64)) - 1ull;
+    q[0] = (uint32_t)lo; q[1] = (uint32_t)(lo >> 32); q[2] = (uint32_t)hi; q[3] = (uint32_t)(hi >> 32);
+}
+
+__device__ __forceinline__ uint32_t config_index(uint64_t seed, uint64_t env, uint32_t episode, int K) {
+    return __umulhi(rng_words(seed, env, episode, STREAM_CONFIG, 0).x, (uint32_t)K);
+}
+
+}  // namespace tpl

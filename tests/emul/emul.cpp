@@ -1,0 +1,148 @@
+// emul.cpp -- host emulation harness for the per-env device logic.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles csrc/piclim_core.cuh + piclim_env.cuh with g++ (tests/emul/host_shim.h stands in for the CUDA
+// intrinsics) and runs the SAME per-env bodies the CUDA kernels run, one env after another, on host
+// arrays.  It lets the CPU-only test tier check the bit-column algorithms, record layout, RNG and
+// afterstate bookkeeping against the oracle before any GPU time is spent.  The product package never
+// loads this library and has no CPU path; entry points mirror tpl_* (minus the stream argument).
+#define TPL_HOST_EMUL 1
+#include "../../reinforcement-learning-for-playing-tetris-with-prescribed-initial-configuration-and-limited-moves_b200/csrc/piclim_env.cuh"
+
+using namespace tpl;
+
+static const uint4 *table() { return reinterpret_cast<const uint4 *>(c_orient); }
+
+struct HostSink {
+    uint32_t *feats; uint8_t *flags; float *ff; size_t n, i;
+    void put(int slot, uint32_t word, uint32_t fl) {
+        const size_t o = (size_t)slot * n + i;
+        if (feats) feats[o] = word;
+        if (flags) flags[o] = (uint8_t)fl;
+        if (ff) { ff[4 * o] = (float)(word & 0xFF); ff[4 * o + 1] = (float)((word >> 8) & 0xFF);
+                  ff[4 * o + 2] = (float)((word >> 16) & 0xFF); ff[4 * o + 3] = (float)(word >> 24); }
+    }
+};
+
+extern "C" {
+
+int emul_pack(void *out, int64_t stride, int aos, int n, const uint16_t *rows, const uint8_t *pieces, int pstride,
+              const uint8_t *npieces, const int32_t *lines, const int32_t *moves, const int8_t *st, const uint8_t *head) {
+    for (int64_t i = 0; i < n; ++i) {
+        Env e;
+        rows_to_cols(rows + i * ROWS, e.col);
+        const int np = npieces[i] < 42 ? npieces[i] : 42;
+        pack_queue(pieces + i * pstride, np, e.q);
+        e.lines = lines ? (uint32_t)lines[i] : 0u; e.moves = moves ? (uint32_t)moves[i] : 0u;
+        e.state = st ? (uint32_t)st[i] : 0u; e.head = head ? head[i] : 0u; e.npieces = (uint32_t)np;
+        if (aos) store_env((uint4 *)out + 4 * i, 1, 0, e); else store_env((uint4 *)out, stride, i, e);
+    }
+    return 0;
+}
+
+int emul_unpack(const void *state, int64_t stride, int n, uint16_t *rows, uint8_t *cur, uint8_t *next, int32_t *lines,
+                int32_t *moves, int8_t *sto, uint8_t *head, uint8_t *npieces, uint8_t *queue) {
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env((const uint4 *)state, stride, i, e);
+        if (rows) cols_to_rows(e.col, rows + i * ROWS);
+        if (cur) cur[i] = e.head < e.npieces ? (uint8_t)queue_piece(e.q, e.head) : (uint8_t)255;
+        if (next) next[i] = e.head + 1 < e.npieces ? (uint8_t)queue_piece(e.q, e.head + 1) : (uint8_t)255;
+        if (lines) lines[i] = (int32_t)e.lines;
+        if (moves) moves[i] = (int32_t)e.moves;
+        if (sto) sto[i] = (int8_t)e.state;
+        if (head) head[i] = (uint8_t)e.head;
+        if (npieces) npieces[i] = (uint8_t)e.npieces;
+        if (queue) for (int p = 0; p < 42; ++p) queue[i * 42 + p] = (uint8_t)queue_piece(e.q, p);
+    }
+    return 0;
+}
+
+int emul_reset_from_pool(void *state, int64_t stride, int n, const void *pool, int K, const int32_t *idx, const uint8_t *mask,
+                         int mode, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count) {
+    uint4 *st = (uint4 *)state;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mode == 1 && !mask[i]) continue;
+        uint32_t ep = episode ? episode[i] : 0u;
+        if (mode == 2) {
+            const uint4 d = st[3 * stride + i];
+            const uint32_t s = d.w & 0xFFu, head = (d.w >> 8) & 0xFFu, np = (d.w >> 16) & 0xFFu;
+            if (s == S_RUNNING && head < np) continue;
+            ep += 1; if (episode) episode[i] = ep;
+        }
+        uint32_t k;
+        if (idx) { const int32_t v = idx[i]; k = (uint32_t)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
+        else k = config_index(seed, env_base + (uint64_t)i, ep, K);
+        Env e; install_config(e, (const uint4 *)pool, k, seed, env_base + (uint64_t)i, ep, gen_count);
+        store_env(st, stride, i, e);
+    }
+    return 0;
+}
+
+int emul_step(void *state, int64_t stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
+              int8_t *sto, int L, int M) {
+    uint4 *st = (uint4 *)state;
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env(st, stride, i, e);
+        int k; bool changed;
+        const uint32_t fl = step_env(e, table(), rot[i], loc[i], L, M, k, changed);
+        if (changed) {
+            st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+            st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+            st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+        }
+        if (!(fl & F_NOPIECE)) st[3 * stride + i] = pack_meta(e);
+        if (dlines) dlines[i] = (int8_t)k;
+        if (flags) flags[i] = (uint8_t)fl;
+        if (sto) sto[i] = (int8_t)e.state;
+    }
+    return 0;
+}
+
+int emul_afterstates(const void *state, int64_t stride, int n, uint8_t *feats, uint8_t *flags, float *ff, int L, int M) {
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env((const uint4 *)state, stride, i, e);
+        HostSink sink{(uint32_t *)feats, flags, ff, (size_t)n, (size_t)i};
+        afterstates_env(e, table(), L, M, sink);
+    }
+    return 0;
+}
+
+int emul_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode, uint32_t episode0) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t q[4];
+        gen_queue(seed, env_base + (uint64_t)i, episode ? episode[i] : episode0, count, q);
+        for (int p = 0; p < count; ++p) out[i * count + p] = (uint8_t)queue_piece(q, p);
+    }
+    return 0;
+}
+
+static int rollout(bool greedy, void *state, int64_t stride, int n, const void *pool, int K, uint32_t *episode, uint32_t *tstep,
+                   long long *stats, int steps, const int32_t *w6, uint64_t seed, uint64_t env_base, int gen_count, int L, int M) {
+    uint4 *st = (uint4 *)state;
+    GreedyWeights gw{};
+    if (greedy) for (int q = 0; q < 6; ++q) gw.w[q] = w6[q];
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint64_t env = env_base + (uint64_t)i;
+        Env e; load_env(st, stride, i, e);
+        uint32_t ep = episode[i], t = tstep[i];
+        for (int s = 0; s < steps; ++s) {
+            if (greedy) rollout_greedy_step(e, ep, t, acc, table(), (const uint4 *)pool, K, seed, env, gen_count, L, M, gw);
+            else rollout_random_step(e, ep, t, acc, table(), (const uint4 *)pool, K, seed, env, gen_count, L, M);
+        }
+        store_env(st, stride, i, e);
+        episode[i] = ep; tstep[i] = t;
+        for (int q = 0; q < 8; ++q) stats[q] += acc[q];
+    }
+    return 0;
+}
+
+int emul_rollout_random(void *state, int64_t stride, int n, const void *pool, int K, uint32_t *episode, uint32_t *tstep,
+                        long long *stats, int steps, uint64_t seed, uint64_t env_base, int gen_count, int L, int M) {
+    return rollout(false, state, stride, n, pool, K, episode, tstep, stats, steps, nullptr, seed, env_base, gen_count, L, M);
+}
+int emul_rollout_greedy(void *state, int64_t stride, int n, const void *pool, int K, uint32_t *episode, uint32_t *tstep,
+                        long long *stats, int steps, const int32_t *w6, uint64_t seed, uint64_t env_base, int gen_count, int L, int M) {
+    return rollout(true, state, stride, n, pool, K, episode, tstep, stats, steps, w6, seed, env_base, gen_count, L, M);
+}
+
+}  // extern "C"
