@@ -104,9 +104,10 @@ int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *po
 
 /* Tetris.move (:354-422) on every env: rot u8[n] (already reduced mod 4 by the caller; rot % n_rot is applied
  * here), loc u8[n] (clamped to 10 - width like :364).  Outputs (each optional): dlines i8[n] rows cleared,
- * flags u8[n] TPL_FLAG_*, st i8[n] state after the move. */
+ * flags u8[n] TPL_FLAG_*, st i8[n] state after the move, stats i64[8] += {episodes ended, wins, top-outs,
+ * move-limit losses, lines, moves placed, steps, 0} (warp-reduced, one atomic per warp and counter). */
 int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc,
-             int8_t *dlines, uint8_t *flags, int8_t *st, int L, int M, void *stream);
+             int8_t *dlines, uint8_t *flags, int8_t *st, long long *stats, int L, int M, void *stream);
 
 /* Afterstate enumeration: slot (r, c) == clone(env).move(r, c) (composition of :354-422), with features on
  * the post-move board (the unchanged board when the move tops out).  feats/flags/feats_f32 as described
@@ -143,6 +144,8 @@ typedef struct tpl_env tpl_env;
 /* Tetris.__init__(L, M, ...) (:141-151) for n envs on CUDA device `device`. */
 int tpl_env_create(tpl_env **out, int n, int L, int M, int device, uint64_t seed, uint64_t env_base);
 void tpl_env_destroy(tpl_env *e);
+/* the reference's L and M are public mutable attributes (:143-144): change them for subsequent calls */
+int tpl_env_set_limits(tpl_env *e, int L, int M);
 /* upload K prescribed reset points (the (board, pieces) tuples of :476-479) */
 int tpl_env_set_pool(tpl_env *e, int K, const uint16_t *rows, const uint8_t *pieces, int pieces_stride,
                      const uint8_t *npieces);

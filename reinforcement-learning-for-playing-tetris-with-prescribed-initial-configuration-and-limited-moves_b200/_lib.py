@@ -18,7 +18,7 @@ DEVICE_API = {
     "pack": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, P, P, P, P, P, P]),
     "unpack": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, P]),
     "reset_from_pool": (c_int, [P, c_int64, c_int, P, c_int, P, P, c_int, P, c_uint64, c_uint64, c_int, P]),
-    "step": (c_int, [P, c_int64, c_int, P, P, P, P, P, c_int, c_int, P]),
+    "step": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, c_int, c_int, P]),
     "afterstates": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P]),
     "gen_pieces": (c_int, [P, c_int, c_int, c_uint64, c_uint64, P, c_uint32, P]),
     "rollout_random": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int, c_int, c_int, P]),
@@ -28,6 +28,7 @@ DEVICE_API = {
 HOST_API = {
     "env_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_uint64, c_uint64]),
     "env_destroy": (None, [c_void_p]),
+    "env_set_limits": (c_int, [c_void_p, c_int, c_int]),
     "env_set_pool": (c_int, [c_void_p, c_int, P, P, c_int, P]),
     "env_reset": (c_int, [c_void_p, P, P, c_int, c_int]),
     "env_load": (c_int, [c_void_p, P, P, c_int, P, P, P, P, P]),

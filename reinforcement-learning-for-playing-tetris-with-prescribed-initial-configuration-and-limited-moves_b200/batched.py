@@ -53,6 +53,7 @@ class BatchedTetris:
             self.stats = torch.zeros(8, dtype=torch.int64, device=self.device)
         self.pool = None
         self.pool_size = 0
+        self.count_stats = True          # move() accumulates episode statistics into self.stats
         self._out = {}
         if config_pool is not None:
             self.set_pool(config_pool)
@@ -160,13 +161,17 @@ class BatchedTetris:
         Returns (rows cleared int8[N], flags uint8[N], state int8[N])."""
         n = self.num_envs
         if isinstance(rot, torch.Tensor):
-            r = torch.remainder(rot.to(self.device), 4).to(torch.uint8)
+            # uint8 tensors go straight to the kernel (it applies rot & 3, and 256 % 4 == 0)
+            r = rot if rot.dtype == torch.uint8 else torch.remainder(rot.to(self.device), 4).to(torch.uint8)
         else:
             r = np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8)
         if isinstance(loc, torch.Tensor):
-            if loc.dtype != torch.uint8 and bool((loc < 0).any()):
-                raise ValueError("location must be >= 0")
-            l = loc.to(self.device).clamp(max=255).to(torch.uint8)
+            if loc.dtype == torch.uint8:
+                l = loc
+            else:
+                if bool((loc < 0).any()):
+                    raise ValueError("location must be >= 0")
+                l = loc.to(self.device).clamp(max=255).to(torch.uint8)
         else:
             la = np.asarray(loc, np.int64)
             if (la < 0).any():
@@ -177,8 +182,7 @@ class BatchedTetris:
         fl = self._buf("mflags", (n,), torch.uint8)
         st = self._buf("mstate", (n,), torch.int8)
         _lib.check(self._L.tpl_step(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
-                                    self.L, self.M, self._stream()), "tpl_step")
-        self.tstep += 1
+                                    _ptr(self.stats) if self.count_stats else None, self.L, self.M, self._stream()), "tpl_step")
         return dl, fl, st
 
     step = move

@@ -87,6 +87,13 @@ void tpl_env_destroy(tpl_env *e) {
     delete e;
 }
 
+int tpl_env_set_limits(tpl_env *e, int L, int M) {
+    if (!e) return fail(TPL_EINVAL, "tpl_env_set_limits: null handle");
+    if (L < 0 || M < 0 || L > 65535 || M > 65535) return fail(TPL_ERANGE, "tpl_env_set_limits: L/M out of range");
+    e->L = L; e->M = M;
+    return 0;
+}
+
 void *tpl_env_state_ptr(tpl_env *e, int64_t *plane_stride) { if (plane_stride) *plane_stride = e->stride; return e->state; }
 void *tpl_env_stream(tpl_env *e) { return (void *)e->stream; }
 
@@ -166,7 +173,7 @@ int tpl_env_move(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dli
     const size_t n = (size_t)e->n;
     CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
-    RC(tpl_step(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, e->L, e->M, e->stream));
+    RC(tpl_step(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->L, e->M, e->stream));
     if (dlines) CU(cudaMemcpyAsync(dlines, e->d_dlines, n, cudaMemcpyDeviceToHost, e->stream));
     if (flags) CU(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, e->stream));
     if (st) CU(cudaMemcpyAsync(st, e->d_st, n, cudaMemcpyDeviceToHost, e->stream));
@@ -232,7 +239,7 @@ int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int
     const size_t n = (size_t)e->n;
     CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
-    RC(tpl_step(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, e->L, e->M, e->stream));
+    RC(tpl_step(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->L, e->M, e->stream));
     RC(tpl_reset_from_pool(e->state, e->stride, e->n, e->pool, e->K, nullptr, nullptr, TPL_RESET_DONE, e->episode, e->seed,
                            e->env_base, 0, e->stream));
     if (dlines) CU(cudaMemcpyAsync(dlines, e->d_dlines, n, cudaMemcpyDeviceToHost, e->stream));

@@ -105,25 +105,42 @@ reset_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, i
 // =================================================================================================
 // step: Tetris.move for every env (game/tetris.py:354-422)
 // =================================================================================================
+__device__ __forceinline__ void flush_stats(const uint32_t (&loc)[8], unsigned long long *stats) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, loc[q]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + q, (unsigned long long)v);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS)
 step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
-            int8_t *dlines, uint8_t *flags, int8_t *sto, int L, int M) {
+            int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats, int L, int M) {
     __shared__ uint4 s_tab[28];
     load_table(s_tab);
     const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
-    if (i >= n) return;
-    Env e; load_env(st, stride, i, e);
-    int k; bool changed;
-    const uint32_t fl = step_env(e, s_tab, rot[i], loc[i], L, M, k, changed);
-    if (changed) {
-        st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
-        st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
-        st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < n) {
+        Env e; load_env(st, stride, i, e);
+        const uint32_t was = e.state;
+        int k; bool changed;
+        const uint32_t fl = step_env(e, s_tab, rot[i], loc[i], L, M, k, changed);
+        if (changed) {
+            st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+            st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+            st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+        }
+        if (!(fl & F_NOPIECE)) st[3 * stride + i] = pack_meta(e);
+        if (dlines) dlines[i] = (int8_t)k;
+        if (flags) flags[i] = (uint8_t)fl;
+        if (sto) sto[i] = (int8_t)e.state;
+        acc[6] = 1; acc[4] = (uint32_t)k; acc[5] = changed ? 1u : 0u;
+        if (was == S_RUNNING && e.state != S_RUNNING) {
+            acc[0] = 1;
+            if (fl & F_WIN) acc[1] = 1; else if (fl & F_TOPOUT) acc[2] = 1; else acc[3] = 1;
+        }
     }
-    if (!(fl & F_NOPIECE)) st[3 * stride + i] = pack_meta(e);
-    if (dlines) dlines[i] = (int8_t)k;
-    if (flags) flags[i] = (uint8_t)fl;
-    if (sto) sto[i] = (int8_t)e.state;
+    if (stats) flush_stats(acc, stats);
 }
 
 // =================================================================================================
@@ -171,14 +188,6 @@ gen_pieces_kernel(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_ba
 // =================================================================================================
 // fused rollouts: state stays in registers for `steps` moves
 // =================================================================================================
-__device__ __forceinline__ void flush_stats(const uint32_t (&loc)[8], unsigned long long *stats) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, loc[q]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + q, (unsigned long long)v);
-    }
-}
-
 template <bool GREEDY>
 __global__ void __launch_bounds__(THREADS)
 rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, int K, uint32_t *episode,
@@ -253,12 +262,13 @@ int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *po
 }
 
 int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
-             int8_t *st, int L, int M, void *stream) {
+             int8_t *st, long long *stats, int L, int M, void *stream) {
     if (n < 0 || !state || !rot || !loc) return fail(TPL_EINVAL, "tpl_step: null argument");
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step: plane_stride < n");
     if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step: L/M out of range");
     if (n == 0) return 0;
-    step_kernel<<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st, L, M);
+    step_kernel<<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
+                                                                    (unsigned long long *)stats, L, M);
     return check_launch("tpl_step");
 }
 

@@ -66,6 +66,10 @@ class HostBatchedTetris:
         except Exception:
             pass
 
+    def set_limits(self, L: int, M: int) -> None:
+        _lib.check(self._L.tpl_env_set_limits(self._h, int(L), int(M)), "tpl_env_set_limits")
+        self.L, self.M = int(L), int(M)
+
     def set_pool(self, pool: ConfigPool) -> None:
         rows = np.ascontiguousarray(pool.rows, np.uint16)
         pieces = np.ascontiguousarray(pool.pieces, np.uint8)

@@ -117,7 +117,12 @@ class Tetris:
         elif fl & (1 | 4):
             self.state = False
 
+    def _sync_limits(self):
+        if (self.L, self.M) != (self._env.L, self._env.M):          # L and M are public mutable attributes (:143-144)
+            self._env.set_limits(self.L, self.M)
+
     def _run_move(self, rotations, location):
+        self._sync_limits()
         n = min(len(self.pieces), MAX_PIECES)
         p = np.zeros((1, MAX_PIECES), np.uint8)
         p[0, :n] = self.pieces[:n]
@@ -140,6 +145,7 @@ class Tetris:
 
     def afterstates(self):
         """(feats uint8[4,10,4] = (rows cleared, holes, bumpiness, aggregate height), flags uint8[4,10])."""
+        self._sync_limits()
         n = min(len(self.pieces), MAX_PIECES)
         p = np.zeros((1, MAX_PIECES), np.uint8)
         p[0, :n] = self.pieces[:n]

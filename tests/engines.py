@@ -212,7 +212,7 @@ class GpuEngine:
         loc = self._t(np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8), np.uint8)
         dl, fl, st = t.zeros(n, dtype=t.int8, device=self.dev), t.zeros(n, dtype=t.uint8, device=self.dev), t.zeros(n, dtype=t.int8, device=self.dev)
         self._chk(self.L.tpl_step(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl), self._p(st),
-                                  L, M, self._stream()), "tpl_step")
+                                  None, L, M, self._stream()), "tpl_step")
         return dl.cpu().numpy(), fl.cpu().numpy(), st.cpu().numpy()
 
     def afterstates(self, s, L, M, f32=False):

@@ -1,0 +1,209 @@
+"""GPU tier: the public Python API (BatchedTetris, HostBatchedTetris, the Tetris facade) and full-size
+size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, piclim_oracle as po
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tp(gpu):
+    import tetris_piclim
+    return tetris_piclim
+
+
+@pytest.fixture(scope="module")
+def carve_pool(tp, golden_dir):
+    return tp.load_pool(os.path.join(golden_dir, "carve_pool_L10_M30.npz"))
+
+
+def test_facade_replays_reference_solutions(tp, carve_pool):
+    """game/main.py:49-57 (test_carving_invertability) against the drop-in facade."""
+    g = tp.Tetris(10, 30, warm_reset=False, debug=True, config_pool=carve_pool, seed=4)
+    for _ in range(5):
+        assert len(g.pieces) == 31 and g.solution
+        for rot, loc in g.solution:
+            g.move(rot, loc)
+        assert g.state is True and g.lines_cleared >= 10
+        g.reset(fresh=True)
+        assert g.state is None and g.moves_used == 0
+    g.terminate()
+
+
+def test_facade_matches_oracle_move_by_move(tp, carve_pool):
+    rng = np.random.default_rng(0)
+    for ep in range(6):
+        g = tp.Tetris(6, 12, warm_reset=False, config_pool=carve_pool, seed=ep)
+        o = po.OracleEnv(6, 12).load(pc.po.rows_from_bool(g.board), g.pieces)
+        b0 = g.board
+        while g.pieces:
+            rot, loc = int(rng.integers(-2, 8)), int(rng.integers(0, 13))
+            g.move(rot, loc); o.move(rot, loc)
+            assert po.rows_from_bool(g.board) == o.rows and g.pieces == o.pieces
+            assert (g.lines_cleared, g.moves_used) == (o.lines_cleared, o.moves_used)
+            assert g.state is {0: None, 1: True, 2: False}[o.state]
+            if len(g.pieces) >= 2:
+                st = g.get_state()
+                assert st[0] is g.board and st[1:3] == (o.pieces[0], o.pieces[1])
+                assert st[3] == 6 - o.lines_cleared and st[4] == 12 - o.moves_used
+        with pytest.raises(IndexError):
+            g.move(0, 0)
+        g.terminate()
+    g = tp.Tetris(6, 12, warm_reset=False, config_pool=carve_pool)
+    with pytest.raises(ValueError):
+        g.move(0, -1)
+    # reference quirk (game/tetris.py:438-443): reset() keeps the counters; attributes are writable
+    g.move(0, 0)
+    g.reset()
+    assert g.moves_used == 1
+    g.board[:, :] = False
+    g.board[-1, 4:] = True
+    g.pieces = [0, 6, 6]
+    g.L, g.lines_cleared, g.moves_used, g.state = 1, 0, 0, None
+    g.move(0, 0)
+    assert g.state is True and not g.board.any()
+    ns = tp.Tetris(6, 12, warm_reset=False, config_pool=carve_pool).next_states()
+    assert 9 <= len(ns) <= 34
+    g.terminate()
+
+
+def test_batched_api_vs_oracle(tp, carve_pool):
+    import torch
+    n, L, M = 5000, 10, 30
+    env = tp.BatchedTetris(n, L, M, seed=21, config_pool=carve_pool, env_base=1000)
+    env.reset()
+    ost = c_oracle.BatchState(n)
+    c_oracle.rollout(ost, 1000, 21, L, M, carve_pool.rows, carve_pool.pieces, carve_pool.npieces, 0, True)
+    rng = np.random.default_rng(1)
+    for t in range(12):
+        feats, flags = env.afterstates()
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=8)
+        assert np.array_equal(feats.cpu().numpy().reshape(n, 40, 4), of)
+        assert np.array_equal(flags.cpu().numpy().reshape(n, 40), ofl)
+        rot, loc = rng.integers(-3, 9, n), rng.integers(0, 14, n)
+        dl, fl, st = env.move(torch.as_tensor(rot), torch.as_tensor(loc)) if t % 2 else env.move(rot, loc)
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        assert np.array_equal(dl.cpu().numpy(), odl) and np.array_equal(st.cpu().numpy(), ost.state)
+        boards, cur, nxt, rem_l, rem_m, state = env.get_state()
+        assert np.array_equal(boards.cpu().numpy(), ost.rows)
+        assert np.array_equal(rem_l.cpu().numpy(), L - ost.lines) and np.array_equal(rem_m.cpu().numpy(), M - ost.moves)
+        has2 = ost.head + 1 < ost.npieces
+        assert np.array_equal(nxt.cpu().numpy()[has2], ost.pieces[np.arange(n), np.minimum(ost.head + 1, 41)][has2])
+    bb = env.get_state(bool_boards=True)[0].cpu().numpy()
+    assert np.array_equal(tp.configs.rows_from_bool(bb), ost.rows)
+    with pytest.raises(ValueError):
+        env.move(np.zeros(n), np.full(n, -1))
+    with pytest.raises(ValueError):
+        env.move(np.zeros(n + 1), np.zeros(n + 1))
+    # explicit boards reset + done_only auto-reset
+    env.reset(done_only=True)
+    f = env.fields()
+    assert not f["state"].any()
+    env.terminate()
+
+
+def test_host_api_vs_oracle(tp, carve_pool):
+    n, L, M = 3000, 10, 30
+    env = tp.HostBatchedTetris(n, L, M, seed=31, env_base=9, config_pool=carve_pool)
+    env.reset()
+    ost = c_oracle.BatchState(n)
+    oep, ots, _ = c_oracle.rollout(ost, 9, 31, L, M, carve_pool.rows, carve_pool.pieces, carve_pool.npieces, 0, True)
+    rng = np.random.default_rng(2)
+    pin = {k: tp.PinnedArray(s, d) for k, (s, d) in dict(rot=((n,), np.uint8), loc=((n,), np.uint8), dl=((n,), np.int8),
+           fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8), afl=((40, n), np.uint8)).items()}
+    for t in range(40):
+        rot, loc = rng.integers(0, 4, n), rng.integers(0, 10, n)
+        pin["rot"].array[:] = rot; pin["loc"].array[:] = loc
+        env.step_observe(*[pin[k].array for k in ("rot", "loc", "dl", "fl", "st", "feats", "afl")])
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        assert np.array_equal(pin["dl"].array, odl) and np.array_equal(pin["st"].array, ost.state)
+        # auto-reset of finished envs, episode e+1 drawn by the counter RNG
+        done = np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]
+        for i in done:
+            oep[i] += 1
+            k = po.config_index(31, 9 + int(i), int(oep[i]), carve_pool.K)
+            ost.rows[i] = carve_pool.rows[k]; ost.pieces[i] = carve_pool.pieces[k]; ost.npieces[i] = carve_pool.npieces[k]
+            ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=8)
+        assert np.array_equal(pin["feats"].array.transpose(1, 0, 2), of)
+        assert np.array_equal(pin["afl"].array.T, ofl)
+    f = env.fields()
+    assert np.array_equal(f["rows"], ost.rows) and np.array_equal(f["moves"], ost.moves)
+    dl, fl, st = env.move(np.zeros(n), np.zeros(n))
+    feats, flags = env.afterstates()
+    assert feats.shape == (n, 4, 10, 4) and flags.shape == (n, 4, 10)
+    env.close()
+
+
+def test_error_codes(tp):
+    import ctypes
+    L = tp._lib.lib()
+    assert L.tpl_step(None, 0, 4, None, None, None, None, None, None, 1, 1, None) == -1
+    assert b"null" in L.tpl_last_error()
+    assert L.tpl_gen_pieces(ctypes.c_void_p(8), 4, 99, 0, 0, None, 0, None) == -2
+    with pytest.raises(tp.TplError):
+        tp._lib.check(L.tpl_afterstates(ctypes.c_void_p(8), 0, 4, None, None, None, 1, 1, None), "x")
+    h = tp.HostBatchedTetris(4, 3, 3)
+    with pytest.raises(tp.TplError):
+        h.reset()                                  # no pool yet
+    h.close()
+
+
+def _torch_features(rows):
+    """Independent torch restatement of (holes, bumpiness, agg height) on uint16 bitrows [N,20]."""
+    import torch
+    r = rows.to(torch.int32)
+    cells = ((r[:, :, None] >> torch.arange(10, device=r.device)) & 1)           # [N,20,10]
+    filled = torch.cummax(cells, dim=1).values                                    # 1 from the first filled row down
+    h = filled.sum(dim=1)                                                         # [N,10]
+    agg = h.sum(dim=1)
+    bump = (h[:, 1:] - h[:, :-1]).abs().sum(dim=1)
+    holes = agg - cells.sum(dim=(1, 2))
+    return holes, bump, agg
+
+
+def test_full_size_properties(tp):
+    """BASELINE config sizes (2^20 envs): size-independent properties instead of an oracle pass.
+    (1) the features promised by afterstates for the slot that is then played equal the features of the board
+        the move really produces; (2) cell conservation: cells' = cells + 4 - 10 * rows_cleared;
+    (3) flags agree with the state transition; (4) the fused rollout equals the same steps done one by one."""
+    import torch
+    n, L, M = 1 << 20, 10, 30
+    pool = tp.synthetic_pool(4096, seed=0, M=M)
+    env = tp.BatchedTetris(n, L, M, seed=0, config_pool=pool)
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    ar = torch.arange(n, device="cuda")
+    for t in range(6):
+        rows0 = env.fields()["rows"].clone()
+        cells0 = _torch_features(rows0)[2] - _torch_features(rows0)[0]
+        feats, flags = env.afterstates()
+        rot = torch.randint(0, 4, (n,), device="cuda", generator=g)
+        loc = torch.randint(0, 10, (n,), device="cuda", generator=g)
+        pf = feats[ar, rot, loc].to(torch.int32)            # promised (dlines, holes, bump, agg)
+        pfl = flags[ar, rot, loc]
+        dl, fl, st = env.move(rot, loc)
+        rows1 = env.fields()["rows"]
+        holes, bump, agg = _torch_features(rows1)
+        assert torch.equal(pf[:, 0], dl.to(torch.int32))
+        assert torch.equal(pf[:, 1], holes.to(torch.int32)) and torch.equal(pf[:, 2], bump.to(torch.int32))
+        assert torch.equal(pf[:, 3], agg.to(torch.int32))
+        assert torch.equal(pfl & 7, fl & 7)
+        top = (fl & 1).bool()
+        cells1 = agg - holes
+        assert torch.equal(cells1[~top], (cells0 + 4 - 10 * dl.to(torch.int64))[~top])
+        assert torch.equal(rows1.view(torch.int16)[top], rows0.view(torch.int16)[top])
+        env.reset(done_only=True)
+    # fused rollout == stepwise path on the same counter-RNG schedule (compared through a checksum of records)
+    a = tp.BatchedTetris(n, L, M, seed=5, config_pool=pool); a.reset()
+    b = tp.BatchedTetris(n, L, M, seed=5, config_pool=pool); b.reset()
+    a.rollout_random(7)
+    a.rollout_random(6)
+    b.rollout_random(13)
+    assert torch.equal(a.state, b.state) and torch.equal(a.stats, b.stats) and torch.equal(a.episode, b.episode)
+    assert int(a.stats[6]) == 13 * n

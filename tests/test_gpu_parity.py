@@ -1,0 +1,69 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against golden fixtures and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pool(golden_dir):
+    z = np.load(os.path.join(golden_dir, "carve_pool_L10_M30.npz"))
+    pieces = np.zeros((len(z["rows"]), 42), np.uint8)
+    pieces[:, :z["pieces"].shape[1]] = z["pieces"]
+    return z["rows"], pieces, z["npieces"]
+
+
+def test_library_loaded(gpu):
+    """The native library is what runs: it must be mapped into this process."""
+    with open("/proc/self/maps") as f:
+        assert "libtetris_piclim_sm100.so" in f.read()
+
+
+def test_golden_kat(gpu, golden_dir):
+    pc.case_golden_kat(gpu, golden_dir)
+
+
+def test_golden_moves(gpu, golden_dir):
+    assert pc.case_golden_moves(gpu, golden_dir) > 2000
+
+
+def test_golden_afterstates(gpu, golden_dir):
+    assert pc.case_golden_afterstates(gpu, golden_dir) >= 300
+
+
+@pytest.mark.parametrize("L,M,seed", [(10, 30, 1), (15, 40, 2), (1, 1, 3), (3, 41, 4)])
+def test_random_moves_vs_oracle(gpu, L, M, seed):
+    pc.case_random_moves(gpu, 100_000, min(M + 3, 34), L, M, seed)
+
+
+@pytest.mark.parametrize("L,M,seed", [(10, 30, 5), (2, 5, 6), (15, 40, 7)])
+def test_afterstates_vs_oracle(gpu, L, M, seed):
+    pc.case_afterstates_vs_oracle(gpu, 100_000, L, M, seed)
+
+
+def test_rng(gpu):
+    pc.case_rng(gpu)
+
+
+def test_reset(gpu, golden_dir):
+    pc.case_reset(gpu, _pool(golden_dir))
+
+
+def test_rollout_random_1e5_episodes(gpu, golden_dir):
+    """>= 1e5 seeded episodes, fused rollout vs the oracle: final boards, queues, counters, episode numbers
+    and the 8 statistics all bit-exact (north-star gate)."""
+    stats = pc.case_rollout(gpu, _pool(golden_dir), 20_000, 150, 10, 30, seed=11, env_base=5_000_000_000, chunks=(0.2, 0.8))
+    assert stats[0] >= 100_000, stats
+
+
+def test_rollout_greedy(gpu, golden_dir):
+    stats = pc.case_rollout(gpu, _pool(golden_dir), 6_000, 90, 10, 30, seed=12, env_base=77,
+                            weights=[760, -360, -180, -510, 100000, -100000], chunks=(0.5, 0.5))
+    assert stats[1] > 0
+
+
+def test_edges(gpu):
+    pc.case_edges(gpu)
