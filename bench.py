@@ -25,7 +25,7 @@ if ROOT not in sys.path:
 
 L_LINES, M_MOVES = 10, 30
 SEED = 0
-ALG_BYTES_AFTERSTATES = 64 + 40 * 4 + 40      # read one 64 B record, write 40 x (4 B features + 1 B flags)
+ALG_BYTES_AFTERSTATES = 64 + 40 * 4           # read one 64 B record, write 40 x 4 B (features with the flags packed in byte 0)
 ALG_BYTES_STEP = 64 + 2 + 64 + 3              # record in, action in, record out, (dlines, flags, state) out
 
 
@@ -176,7 +176,7 @@ def workload_config(args, n_total):
     return {"workload": "2^20 envs/GPU x [40-slot afterstate enumeration + features -> move -> auto-reset], "
                         "prescribed-config pool (4096 synthetic + 256 carve), L=10 M=30 (BASELINE configs[2]; configs[4] at 8 GPUs)",
             "envs_per_gpu": args.envs_per_gpu, "envs_total": n_total, "L": L_LINES, "M": M_MOVES, "pool": 4352,
-            "l2": "working set per step (64 MiB state r+w, 200 MiB afterstate outputs) exceeds the 126 MB L2",
+            "l2": "working set per step (64 MiB state r+w, 160 MiB afterstate outputs) exceeds the 126 MB L2",
             "parallelism": f"envs sharded by global env id over {args.gpus} GPU(s); one 64-byte NCCL all-reduce per rollout"}
 
 
@@ -214,7 +214,7 @@ def run_b200(args):
     loc = torch.randint(0, 10, (total, n), device=dev, dtype=torch.uint8, generator=g)
 
     def one_step(i, ev=None):
-        env.afterstates()
+        env.afterstates(packed=True)
         if ev: ev[1].record()
         env.move(rot[i], loc[i])
         if ev: ev[2].record()
@@ -250,10 +250,10 @@ def run_b200(args):
     henv = tp.HostBatchedTetris(n, L_LINES, M_MOVES, device=local, seed=SEED, env_base=rank * n, config_pool=pool)
     henv.reset()
     pin = {k: tp.PinnedArray(s, d) for k, (s, d) in dict(rot=((n,), np.uint8), loc=((n,), np.uint8), dl=((n,), np.int8),
-           fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8), afl=((40, n), np.uint8)).items()}
+           fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8)).items()}
     hrot, hloc = rot.cpu().numpy(), loc.cpu().numpy()
     e2e_steps = max(3, min(K, 10))
-    bufs = [pin[k].array for k in ("rot", "loc", "dl", "fl", "st", "feats", "afl")]
+    bufs = [pin[k].array for k in ("rot", "loc", "dl", "fl", "st", "feats")] + [None]      # compact afterstate form
     for i in range(2):
         pin["rot"].array[:] = hrot[i]; pin["loc"].array[:] = hloc[i]
         henv.step_observe(*bufs)
@@ -289,7 +289,7 @@ def run_b200(args):
             "reset_done": {"ms": k_ms[2]},
         },
         "e2e": {"value": n_total * 40 * e2e_steps / e2e_s, "unit": "afterstates/s", "env_steps_per_sec": n_total * e2e_steps / e2e_s,
-                "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 203 * n, "steps": e2e_steps,
+                "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 163 * n, "steps": e2e_steps,
                 "api": "tpl_env_step_observe (host-buffer C ABI, pinned buffers)"},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
@@ -313,12 +313,12 @@ def extra_single_gpu(tp, torch, dev, pool, args):
     s = torch.cuda.Stream(device=dev)
     iters = 1000
     with torch.cuda.stream(s):
-        env.afterstates()
+        env.afterstates(packed=True)
         s.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
             for _ in range(iters):
-                env.afterstates()
+                env.afterstates(packed=True)
         g.replay(); s.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s); g.replay(); e1.record(s); s.synchronize()

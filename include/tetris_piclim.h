@@ -110,8 +110,11 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
              int8_t *dlines, uint8_t *flags, int8_t *st, long long *stats, int L, int M, void *stream);
 
 /* Afterstate enumeration: slot (r, c) == clone(env).move(r, c) (composition of :354-422), with features on
- * the post-move board (the unchanged board when the move tops out).  feats/flags/feats_f32 as described
- * above; any of the three may be NULL. */
+ * the post-move board (the unchanged board when the move tops out).  Output forms (slot-major, see above):
+ *   feats + flags            parity form, 200 B/env: feats byte 0 = rows cleared, flags separate
+ *   feats only (flags NULL)  compact form, 160 B/env: feats byte 0 = rows cleared | flags << 3
+ *   feats_f32 + flags        value-net form (float4 per slot); may be combined with feats
+ * n <= 2^25 per call. */
 int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *feats, uint8_t *flags,
                     float *feats_f32, int L, int M, void *stream);
 

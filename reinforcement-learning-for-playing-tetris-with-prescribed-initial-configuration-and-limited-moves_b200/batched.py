@@ -213,21 +213,26 @@ class BatchedTetris:
         return out
 
     # ------------------------------------------------------------------ afterstates (F)
-    def afterstates(self, f32: bool = False, u8: bool = True):
+    def afterstates(self, f32: bool = False, u8: bool = True, packed: bool = False):
         """All 40 afterstates of every env: slot (r, c) == clone(env).move(r, c).
 
         Returns (feats, flags[, feats_f32]): ``feats`` uint8 viewed as [N, 4, 10, 4] = (rows cleared, holes,
         bumpiness, aggregate height), ``flags`` uint8 [N, 4, 10]; both are strided views of slot-major buffers
         ([40, N, 4] / [40, N]) so no copy is made.  ``feats_f32`` (if requested) is float32 [40*N, 4] in
-        slot-major row order (row s*N + i), ready to be fed to the value net."""
+        slot-major row order (row s*N + i), ready to be fed to the value net.
+
+        ``packed=True`` is the compact 160 B/env form: only ``feats`` is written and its byte 0 holds
+        ``rows cleared | flags << 3``; returns (feats, None)."""
         n = self.num_envs
-        feats = self._buf("feats", (40, n, 4), torch.uint8) if u8 else None
-        flags = self._buf("aflags", (40, n), torch.uint8)
+        if packed and f32:
+            raise ValueError("the packed form has no float output")
+        feats = self._buf("feats", (40, n, 4), torch.uint8) if (u8 or packed) else None
+        flags = None if packed else self._buf("aflags", (40, n), torch.uint8)
         ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
         _lib.check(self._L.tpl_afterstates(_ptr(self.state), self.stride, n, _ptr(feats), _ptr(flags), _ptr(ff), self.L, self.M,
                                            self._stream()), "tpl_afterstates")
-        fv = feats.view(4, 10, n, 4).permute(2, 0, 1, 3) if u8 else None
-        gv = flags.view(4, 10, n).permute(2, 0, 1)
+        fv = feats.view(4, 10, n, 4).permute(2, 0, 1, 3) if feats is not None else None
+        gv = flags.view(4, 10, n).permute(2, 0, 1) if flags is not None else None
         return (fv, gv, ff) if f32 else (fv, gv)
 
     # ------------------------------------------------------------------ fused rollouts

@@ -32,16 +32,19 @@ enum : uint32_t { F_TOPOUT = 1, F_WIN = 2, F_LOSE = 4, F_ALIAS = 8, F_NOPIECE = 
 enum : uint32_t { S_RUNNING = 0, S_WON = 1, S_LOST = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// A. orientation table.  One uint4 per (piece, rot 0..3); rot >= n_rot repeats rot % n_rot (:61).
-//   x: bits 0-15  cb   : 4-bit column images, nibble j = shape column j, bit i = cell i rows above
+// A. orientation table.  Two uint4 per (piece, rot 0..3); rot >= n_rot repeats rot % n_rot (:61).
+//   a.x: bits 0-15 cb  : 4-bit column images, nibble j = shape column j, bit i = cell i rows above
 //                        the shape's bottom row
-//      bits 16-18 w, bits 20-22 h, bits 24-25 n_rot-1, bit 28 = rot is an alias (rot >= n_rot)
-//   y: bo bytes: byte j = rows between the shape's bottom row and the lowest cell of column j
-//      (= h-1-profile[j] with profile the tuple at :25-55); 64 for j >= w so it never wins the max
-//   z: to bytes: byte j = (height of the highest cell of column j above the bottom row) + 1
-//   w: bo nibbles (4 bits per column, no sentinel) in bits 0-15 -- used by the column-aligned path
+//        bits 16-18 w, bits 20-22 h, bits 24-25 n_rot-1, bit 28 = rot is an alias (rot >= n_rot)
+//   a.y: bo bytes: byte j = rows between the shape's bottom row and the lowest cell of column j
+//        (= h-1-profile[j] with profile the tuple at :25-55); 64 for j >= w so it never wins the max
+//   a.z: (to0, to1) as s16x2, to_j = (height of the highest cell of column j above the bottom row) + 1,
+//        -64 for j >= w so that max(H_j, y + to_j) leaves the column height alone
+//   a.w: (to2, to3) as s16x2
+//   b.x: bo nibbles (4 bits per column, no sentinel) -- used by the column-aligned general path
+//   b.y: (1 << h) - 1      b.z: 20 - h (top-out iff y > 20 - h)      b.w: unused
 // ---------------------------------------------------------------------------------------------
-struct OrientEntry { uint32_t x, y, z, w; };
+struct OrientEntry { uint32_t ax, ay, az, aw, bx, by, bz, bw; };
 
 constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool alias) {
     int m[4] = {m0, m1, m2, m3};
@@ -50,7 +53,8 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
         if (m[i]) h = i + 1;
         for (int j = 0; j < 4; ++j) if ((m[i] >> j) & 1) { if (j + 1 > w) w = j + 1; }
     }
-    uint32_t cb = 0, bo = 0, to = 0, bon = 0;
+    uint32_t cb = 0, bo = 0, bon = 0;
+    uint32_t to[4] = {0xFFC0u, 0xFFC0u, 0xFFC0u, 0xFFC0u};      // -64 as s16
     for (int j = 0; j < 4; ++j) {
         if (j >= w) { bo |= 64u << (8 * j); continue; }
         int lowest = -1, highest = -1;
@@ -60,10 +64,11 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
         }
         bo |= (uint32_t)(h - 1 - lowest) << (8 * j);
         bon |= (uint32_t)(h - 1 - lowest) << (4 * j);
-        to |= (uint32_t)(h - highest) << (8 * j);
+        to[j] = (uint32_t)(h - highest);
     }
     return OrientEntry{cb | ((uint32_t)w << 16) | ((uint32_t)h << 20) | ((uint32_t)(nrot - 1) << 24) | (alias ? 1u << 28 : 0u),
-                       bo, to, bon};
+                       bo, to[0] | (to[1] << 16), to[2] | (to[3] << 16),
+                       bon, (1u << h) - 1u, (uint32_t)(20 - h), 0u};
 }
 
 // row masks top->bottom, bit j = shape column j, exactly the arrays at game/tetris.py:25-55
@@ -86,6 +91,9 @@ __constant__ OrientEntry c_orient[28] = {
 };
 #undef TPL_O
 
+constexpr int TAB_WORDS4 = 56;      // 28 entries x 2 uint4
+
+// `o` below is the first uint4 (a) of an entry, `ob` the second (b)
 __device__ __forceinline__ int orient_w(const uint4 &o) { return (o.x >> 16) & 7; }
 __device__ __forceinline__ int orient_h(const uint4 &o) { return (o.x >> 20) & 7; }
 __device__ __forceinline__ int orient_nrot(const uint4 &o) { return ((o.x >> 24) & 3) + 1; }
@@ -136,7 +144,28 @@ __device__ __forceinline__ uint32_t queue_piece(const uint32_t (&q)[4], uint32_t
     return __funnelshift_r(lo, hi, off) & 7u;
 }
 
-__device__ __forceinline__ int col_height(uint32_t c) { return 32 - __clz(c); }
+// height of a bit-column = index of its highest set bit + 1 (bfind returns -1 for 0): one FLO + one add
+__device__ __forceinline__ int col_height(uint32_t c) {
+#ifdef TPL_HOST_EMUL
+    return 32 - __clz(c);
+#else
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(c));
+    return r + 1;
+#endif
+}
+
+// a * b on the FMA pipe (IMAD): used for `bits << y` as bits * (1 << y) so the variable shifts do not all
+// land on the ALU pipe, which is the pipe that bounds the afterstate kernel
+__device__ __forceinline__ uint32_t mul_fma_pipe(uint32_t a, uint32_t b) {
+#ifdef TPL_HOST_EMUL
+    return a * b;
+#else
+    uint32_t r;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // C. the general move on bit-columns (any loc, static column indexing only).
@@ -144,12 +173,12 @@ __device__ __forceinline__ int col_height(uint32_t c) { return 32 - __clz(c); }
 // ---------------------------------------------------------------------------------------------
 struct MoveOut { int k; bool topout; };
 
-__device__ __forceinline__ MoveOut place_general(uint32_t (&x)[COLS], const uint4 &o, int loc_raw) {
+__device__ __forceinline__ MoveOut place_general(uint32_t (&x)[COLS], const uint4 &o, const uint4 &ob, int loc_raw) {
     const int w = orient_w(o), h = orient_h(o);
     const int loc = min(loc_raw, COLS - w);                                  // :364
     // align the piece's 4-bit column images / bottom offsets with the board columns
     const uint64_t PB = (uint64_t)(o.x & 0xFFFFu) << (4 * loc);
-    const uint64_t BO = (uint64_t)(o.w & 0xFFFFu) << (4 * loc);
+    const uint64_t BO = (uint64_t)(ob.x & 0xFFFFu) << (4 * loc);
     uint32_t pk[COLS];
     int y = 0;
 #pragma unroll

@@ -50,6 +50,7 @@ __device__ __forceinline__ void install_config(Env &e, const uint4 *__restrict__
 
 // ---------------------------------------------------------------------------------------------
 // step: Tetris.move (game/tetris.py:354-422).  Returns the TPL_FLAG_* bits; k = rows cleared.
+// tab: 28 entries x 2 uint4 (see piclim_core.cuh)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t rot, uint32_t loc, int L, int M, int &k,
                                              bool &board_changed) {
@@ -57,8 +58,8 @@ __device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t 
     if (e.head >= e.npieces) return F_NOPIECE;
     const uint32_t piece = queue_piece(e.q, e.head);                        // :356 pop(0)
     e.head += 1;
-    const uint4 o = tab[piece * 4 + (rot & 3u)];                            // :359 / :61
-    const MoveOut m = place_general(e.col, o, (int)loc);
+    const uint32_t t = (piece * 4 + (rot & 3u)) * 2;                        // :359 / :61
+    const MoveOut m = place_general(e.col, tab[t], tab[t + 1], (int)loc);
     k = m.k; board_changed = !m.topout;
     return apply_outcome(e, m, L, M);
 }
@@ -66,7 +67,70 @@ __device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // afterstates: slot (r, c) == clone(env).move(r, c); sink.put(slot, word, flags) with
 //   word = dlines | holes << 8 | bumpiness << 16 | aggregate_height << 24
+//
+// Fast path (no row clears), per slot, all on packed bytes / halfwords:
+//   y      = max_j(H[c+j] - bo_j)                          hard drop in height form (:424-433)
+//   full   = A[c] & ((col[c+j] | cb_j << y) for j<4) & (hm << y)   rows of the piece that become full (:382-386)
+//   N      = max(H[c+j], y + to_j)  (s16x2 add-max, -64 sentinel keeps columns the piece does not cover)
+//   agg'   = agg + sum_j (N_j - H_j)                        one VABSDIFF4.U8.ACC
+//   bump'  = bump - old pairs + new pairs                   one VABSDIFF4.U8.ACC + one VABSDIFF
+//   holes' = agg' - (cells + 4)
+// Slots whose placement completes a row are deferred to the general move below (rare per slot).
 // ---------------------------------------------------------------------------------------------
+// static byte-permute selectors: X = (H[c-1], n0, n1, n2) from (N4, Hprev); Y = (n0, n1, n2, n3) from N4;
+// pairs that touch a column >= 10 are made degenerate (|a - a| = 0) so they never count.
+__host__ __device__ constexpr uint32_t sel_x(int c) {
+    return c == 0 ? 0x2100u : c <= 7 ? 0x2104u : c == 8 ? 0x1104u : 0x0004u;
+}
+__host__ __device__ constexpr uint32_t sel_y(int c) {
+    return c <= 6 ? 0x3210u : c == 7 ? 0x2210u : c == 8 ? 0x1110u : 0x0000u;
+}
+
+// sum over the window pairs (H[c-1],n0),(n0,n1),(n1,n2),(n2,n3),(n3,H[c+4]) restricted to columns 0..9
+template <int C>
+__device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, uint32_t hnext, uint32_t acc) {
+    const uint32_t X = __byte_perm(N4, hprev, sel_x(C));
+    const uint32_t Y = (C <= 6) ? N4 : __byte_perm(N4, 0u, sel_y(C));
+    uint32_t s = __vsadu4(X, Y) + acc;
+    if (C + 4 <= 9) s = __sad((int)(N4 >> 24), (int)hnext, s);
+    return s;
+}
+
+template <int C, class Sink>
+__device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS], const uint32_t (&col)[14],
+                                          const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
+                                          uint32_t flN, uint32_t flT, bool canon, int w,
+                                          int bo0, int bo1, int bo2, int bo3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
+                                          uint32_t TO01, uint32_t TO23, uint32_t hm, int thr,
+                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask) {
+    const int y = max(max(H[C] - bo0, H[C + 1] - bo1), max(H[C + 2] - bo2, H[C + 3] - bo3));
+    const bool top = y > thr;
+    const uint32_t pw = 1u << y;
+    const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & (col[C] | mul_fma_pipe(cb0, pw)) & (col[C + 1] | mul_fma_pipe(cb1, pw)) &
+                          (col[C + 2] | mul_fma_pipe(cb2, pw)) & (col[C + 3] | mul_fma_pipe(cb3, pw));
+    const uint32_t Y2 = (uint32_t)y * 0x10001u;
+    const uint32_t N01 = __viaddmax_s16x2(Y2, TO01, __byte_perm(Hw[C], 0u, 0x4140));
+    const uint32_t N23 = __viaddmax_s16x2(Y2, TO23, __byte_perm(Hw[C], 0u, 0x4342));
+    const uint32_t N4 = __byte_perm(N01, N23, 0x6420);
+    const uint32_t agg2 = __vsadu4(N4, Hw[C]) + agg;
+    const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
+    uint32_t wnew = agg2 * 0x01000100u + K;
+    wnew = b2 * 0x10000u + wnew;
+    wnew = top ? U : wnew;
+    const uint32_t fnew = top ? flT : flN;
+    const bool pnew = !top && full != 0u;
+    if (C <= 6) {                                  // every width fits (w <= 4)
+        word = wnew; fl = fnew; pend = pnew;
+    } else {                                       // loc clamps to 10 - w (:364): repeat the last fitting column
+        const bool fits = C + w <= COLS;
+        word = fits ? wnew : word;
+        fl = fits ? fnew : (fl | F_ALIAS);
+        pend = fits ? pnew : pend;
+    }
+    if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
+    if (!pend) sink.put(r * 10 + C, word, fl);
+}
+
 template <class Sink>
 __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, int L, int M, Sink &sink) {
     if (e.head >= e.npieces) {
@@ -75,30 +139,32 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
     }
     const uint32_t piece = queue_piece(e.q, e.head);
 
-    // per-env precompute, shared by all 40 slots.  Column k lives at index k (col) / k+1 (H); the padding
-    // entries are neutral (full columns for the AND, height 0) and every use of them is statically excluded.
-    uint32_t col[14]; int H[15];
-    H[0] = 0;
-    int agg = 0, cells = 0;
+    // ---- per-env precompute, shared by all 40 slots.  Indices 10..13 are neutral padding (full columns for
+    //      the AND, height 0); every use of them in a pair sum is statically excluded.
+    uint32_t col[14]; int H[14];
+    uint32_t cells = 0;
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) {
-        col[k] = e.col[k]; H[k + 1] = col_height(col[k]);
-        agg += H[k + 1]; cells += __popc(col[k]);
+    for (int k = 0; k < COLS; ++k) { col[k] = e.col[k]; H[k] = col_height(col[k]); cells += __popc(col[k]); }
+#pragma unroll
+    for (int k = COLS; k < 14; ++k) { col[k] = COL_FULL; H[k] = 0; }
+    const uint32_t HB0 = H[0] | (H[1] << 8) | (H[2] << 16) | (H[3] << 24);
+    const uint32_t HB1 = H[4] | (H[5] << 8) | (H[6] << 16) | (H[7] << 24);
+    const uint32_t HB2 = H[8] | (H[9] << 8);
+    uint32_t Hw[COLS];                               // Hw[c] = bytes (H[c], H[c+1], H[c+2], H[c+3])
+    Hw[0] = HB0; Hw[4] = HB1; Hw[8] = HB2;
+    Hw[1] = __byte_perm(HB0, HB1, 0x4321); Hw[2] = __byte_perm(HB0, HB1, 0x5432); Hw[3] = __byte_perm(HB0, HB1, 0x6543);
+    Hw[5] = __byte_perm(HB1, HB2, 0x4321); Hw[6] = __byte_perm(HB1, HB2, 0x5432); Hw[7] = __byte_perm(HB1, HB2, 0x6543);
+    Hw[9] = HB2 >> 8;
+    const uint32_t agg = __vsadu4(HB0, 0u) + __vsadu4(HB1, 0u) + __vsadu4(HB2, 0u);
+    const uint32_t bump = __vsadu4(Hw[0], Hw[1]) + __vsadu4(Hw[4], Hw[5]) + (uint32_t)__sad(H[8], H[9], 0u);
+    uint32_t Bb[COLS];                               // bump minus the pairs a placement at c can change
+    {
+        uint32_t t;
+#define TPL_BB(C) t = window_pairs<C>(Hw[C], (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], 0u); Bb[C] = bump - t;
+        TPL_BB(0) TPL_BB(1) TPL_BB(2) TPL_BB(3) TPL_BB(4) TPL_BB(5) TPL_BB(6) TPL_BB(7) TPL_BB(8) TPL_BB(9)
+#undef TPL_BB
     }
-#pragma unroll
-    for (int k = COLS; k < 14; ++k) { col[k] = COL_FULL; H[k + 1] = 0; }
-    int D[9]; int bump = 0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { D[k] = abs(H[k + 1] - H[k + 2]); bump += D[k]; }
-    int oldB[COLS];
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-        int s = 0;
-#pragma unroll
-        for (int k = c - 1; k <= c + 3; ++k) if (k >= 0 && k <= 8) s += D[k];
-        oldB[c] = s;
-    }
-    uint32_t pre[11], suf[11], A[COLS];
+    uint32_t pre[11], suf[11], A[COLS];              // A[c] = AND of the columns outside [c, c+3]
     pre[0] = COL_FULL; suf[10] = COL_FULL;
 #pragma unroll
     for (int k = 0; k < COLS; ++k) pre[k + 1] = pre[k] & col[k];
@@ -107,64 +173,40 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
 #pragma unroll
     for (int c = 0; c < COLS; ++c) A[c] = pre[c] & suf[c + 4 < 10 ? c + 4 : 10];
 
-    const uint32_t U = ((uint32_t)(agg - cells) << 8) | ((uint32_t)bump << 16) | ((uint32_t)agg << 24);
+    const uint32_t U = ((agg - cells) << 8) | (bump << 16) | (agg << 24);   // unchanged board (top-out slots)
+    const uint32_t K = 0u - ((cells + 4u) << 8);                             // holes' = agg' - (cells + 4)
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
     unsigned long long pending = 0ull;
 
     for (int r = 0; r < 4; ++r) {
-        const uint4 o = tab[piece * 4 + r];
-        const int w = orient_w(o), h = orient_h(o);
+        const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
+        const int w = orient_w(o);
         const int bo0 = o.y & 0xFF, bo1 = (o.y >> 8) & 0xFF, bo2 = (o.y >> 16) & 0xFF, bo3 = o.y >> 24;
-        const int to0 = o.z & 0xFF, to1 = (o.z >> 8) & 0xFF, to2 = (o.z >> 16) & 0xFF, to3 = o.z >> 24;
         const uint32_t cb0 = o.x & 15u, cb1 = (o.x >> 4) & 15u, cb2 = (o.x >> 8) & 15u, cb3 = (o.x >> 12) & 15u;
-        const uint32_t hm = (1u << h) - 1u;
         const uint32_t afl = orient_alias(o) ? F_ALIAS : 0u;
-        uint32_t word = 0, fl = 0; bool pend = false;
-#pragma unroll
-        for (int c = 0; c < COLS; ++c) {
-            if (c + w <= COLS) {
-                // B: hard drop in height form: y = rows below the shape's bottom row
-                const int y = max(max(H[c + 1] - bo0, H[c + 2] - bo1), max(H[c + 3] - bo2, H[c + 4] - bo3));
-                const bool top = (y + h > ROWS);
-                const uint32_t full = A[c] & (col[c] | (cb0 << y)) & (col[c + 1] | (cb1 << y)) &
-                                      (col[c + 2] | (cb2 << y)) & (col[c + 3] | (cb3 << y)) & (hm << y);
-                // incremental features when no row clears
-                const int n0 = y + to0;
-                const int n1 = (w > 1) ? y + to1 : H[c + 2];
-                const int n2 = (w > 2) ? y + to2 : H[c + 3];
-                const int n3 = (w > 3) ? y + to3 : H[c + 4];
-                const int a2 = agg - (H[c + 1] + H[c + 2] + H[c + 3] + H[c + 4]) + (n0 + n1 + n2 + n3);
-                int nb = 0;
-                if (c >= 1) nb += abs(H[c] - n0);
-                if (c + 1 <= 9) nb += abs(n0 - n1);
-                if (c + 2 <= 9) nb += abs(n1 - n2);
-                if (c + 3 <= 9) nb += abs(n2 - n3);
-                if (c + 4 <= 9) nb += abs(n3 - H[c + 5]);
-                const int b2 = bump - oldB[c] + nb;
-                word = ((uint32_t)(a2 - cells - 4) << 8) | ((uint32_t)b2 << 16) | ((uint32_t)a2 << 24);
-                fl = fl_noclear; pend = false;
-                if (top) { word = U; fl = F_TOPOUT; }
-                else if (full) { pend = true; if (!afl) pending |= 1ull << (r * 10 + c); }
-            } else {
-                fl |= F_ALIAS;
-            }
-            if (!pend) sink.put(r * 10 + c, word, fl | afl);
-        }
+        const bool canon = afl == 0u;
+        const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
+        uint32_t word = 0, fl = 0, pmask = 0; bool pend = false;
+#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, K, U, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
+                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask);
+        TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
+#undef TPL_SLOT
+        pending |= (unsigned long long)pmask << (10 * r);
     }
 
-    // deferred line-clear slots (rare per slot, so kept out of the unrolled fast path)
+    // ---- deferred line-clear slots: the general move on a copy of the columns
     while (pending) {
         const int s = __ffsll((long long)pending) - 1;
         pending &= pending - 1ull;
         const int r = s / 10, c = s - 10 * r;
-        const uint4 o = tab[piece * 4 + r];
+        const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
         uint32_t x[COLS];
 #pragma unroll
         for (int k = 0; k < COLS; ++k) x[k] = e.col[k];
-        const MoveOut m = place_general(x, o, c);
-        const uint32_t f3 = board_features(x, cells + 4 - 10 * m.k);
+        const MoveOut m = place_general(x, o, ob, c);
+        const uint32_t f3 = board_features(x, (int)cells + 4 - 10 * m.k);
         const uint32_t word = (uint32_t)m.k | (f3 << 8);
-        const uint32_t fl = ((int)e.lines + m.k >= L) ? F_WIN : fl_noclear;   // :415-422
+        const uint32_t fl = m.k == 0 ? fl_noclear : (((int)e.lines + m.k >= L) ? F_WIN : fl_noclear);   // :389-391, :415-422
         const int nrot = orient_nrot(o), w = orient_w(o);
         const int cend = (c == COLS - w) ? COLS - 1 : c;
         for (int r2 = r; r2 < 4; r2 += nrot)

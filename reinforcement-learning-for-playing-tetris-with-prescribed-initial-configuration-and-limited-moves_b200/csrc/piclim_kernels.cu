@@ -32,7 +32,7 @@ long long launches() { return g_launches.load(); }
 const char *last_error() { return g_err; }
 
 __device__ __forceinline__ void load_table(uint4 *s_tab) {
-    if (threadIdx.x < 28) s_tab[threadIdx.x] = reinterpret_cast<const uint4 *>(c_orient)[threadIdx.x];
+    if (threadIdx.x < TAB_WORDS4) s_tab[threadIdx.x] = reinterpret_cast<const uint4 *>(c_orient)[threadIdx.x];
     __syncthreads();
 }
 
@@ -105,22 +105,29 @@ reset_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, i
 // =================================================================================================
 // step: Tetris.move for every env (game/tetris.py:354-422)
 // =================================================================================================
+// Episode statistics: per-thread counters -> warp shuffle-reduce -> shared-memory atomics -> one global atomic
+// per counter and CTA.  (One global atomic per warp serialised ~33k same-address atomics per counter at 2^20
+// envs and took 3x longer than the step kernel itself.)
 __device__ __forceinline__ void flush_stats(const uint32_t (&loc)[8], unsigned long long *stats) {
+    __shared__ unsigned int s_acc[8];
+    if (threadIdx.x < 8) s_acc[threadIdx.x] = 0u;
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, loc[q]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + q, (unsigned long long)v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_acc[q], v);
     }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_acc[threadIdx.x]) atomicAdd(stats + threadIdx.x, (unsigned long long)s_acc[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(THREADS)
 step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
             int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats, int L, int M) {
-    __shared__ uint4 s_tab[28];
+    __shared__ uint4 s_tab[TAB_WORDS4];
     load_table(s_tab);
-    const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (i < n) {
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
         Env e; load_env(st, stride, i, e);
         const uint32_t was = e.state;
         int k; bool changed;
@@ -134,10 +141,10 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
         if (dlines) dlines[i] = (int8_t)k;
         if (flags) flags[i] = (uint8_t)fl;
         if (sto) sto[i] = (int8_t)e.state;
-        acc[6] = 1; acc[4] = (uint32_t)k; acc[5] = changed ? 1u : 0u;
+        acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
         if (was == S_RUNNING && e.state != S_RUNNING) {
-            acc[0] = 1;
-            if (fl & F_WIN) acc[1] = 1; else if (fl & F_TOPOUT) acc[2] = 1; else acc[3] = 1;
+            acc[0] += 1;
+            if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
         }
     }
     if (stats) flush_stats(acc, stats);
@@ -146,30 +153,37 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
 // =================================================================================================
 // afterstates: slot (r, c) == clone(env).move(r, c), features on the post-move board
 // =================================================================================================
-template <bool WITH_U8, bool WITH_F32>
+// Output modes: 0 = words only, flags packed into byte 0 (dlines | flags << 3): the compact 160 B/env form;
+//               1 = words (byte 0 = dlines) + separate flags array: the 200 B/env parity form;
+//               2 = float4 features + flags (value-net input rows);   3 = all three.
+// All arrays are slot-major [40][n]; element (slot, i) sits at offset slot * n + i in each of them, so one
+// 32-bit offset serves every array and a warp's store of one slot is one contiguous 128-byte line.
+template <int MODE>
 struct GlobalSink {
-    uint32_t *feats; uint8_t *flags; float4 *ff; size_t n, i;
+    uint32_t *words; uint8_t *flags; float4 *ff;      // already offset by the env index
+    uint32_t n;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
-        const size_t o = (size_t)slot * n + i;
-        if (WITH_U8) { if (feats) feats[o] = word; }
-        if (flags) flags[o] = (uint8_t)fl;
-        if (WITH_F32)
+        const uint32_t o = (uint32_t)slot * n;
+        if (MODE == 0) words[o] = word | (fl << 3);
+        if (MODE == 1 || MODE == 3) words[o] = word;
+        if (MODE >= 1) flags[o] = (uint8_t)fl;
+        if (MODE >= 2)
             ff[o] = make_float4((float)(word & 0xFFu), (float)((word >> 8) & 0xFFu), (float)((word >> 16) & 0xFFu),
                                 (float)(word >> 24));
     }
 };
 
-template <bool WITH_U8, bool WITH_F32>
+template <int MODE>
 __global__ void __launch_bounds__(THREADS)
-afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ feats,
+afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
-    __shared__ uint4 s_tab[28];
+    __shared__ uint4 s_tab[TAB_WORDS4];
     load_table(s_tab);
-    const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
-    if (i >= n) return;
-    Env e; load_env(st, stride, i, e);
-    GlobalSink<WITH_U8, WITH_F32> sink{feats, flags, ff, (size_t)n, (size_t)i};
-    afterstates_env(e, s_tab, L, M, sink);
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+        Env e; load_env(st, stride, i, e);
+        GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n};
+        afterstates_env(e, s_tab, L, M, sink);
+    }
 }
 
 // =================================================================================================
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(THREADS)
 rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, int K, uint32_t *episode,
                uint32_t *tstep, unsigned long long *stats, int steps, uint64_t seed, uint64_t env_base,
                int gen_count, int L, int M, GreedyWeights gw) {
-    __shared__ uint4 s_tab[28];
+    __shared__ uint4 s_tab[TAB_WORDS4];
     load_table(s_tab);
     const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -219,6 +233,19 @@ rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool,
 using namespace tpl;
 
 static inline unsigned grid_for(int n) { return (unsigned)((n + THREADS - 1) / THREADS); }
+
+// Grid-stride kernels: at most `blocks_per_sm` resident CTAs per SM, i.e. a multiple of the SM count (148 on
+// B200), so per-CTA set-up and the statistics flush are paid once per CTA slot instead of once per 128 envs.
+static unsigned grid_persistent(int n, int blocks_per_sm) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    if (blocks_per_sm <= 0) blocks_per_sm = 16;
+    const unsigned need = grid_for(n), cap = (unsigned)(sms * blocks_per_sm);
+    return need < cap ? need : cap;
+}
 
 extern "C" {
 
@@ -267,7 +294,7 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step: plane_stride < n");
     if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step: L/M out of range");
     if (n == 0) return 0;
-    step_kernel<<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
+    step_kernel<<<grid_persistent(n, 16), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
                                                                     (unsigned long long *)stats, L, M);
     return check_launch("tpl_step");
 }
@@ -276,18 +303,17 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
                     void *stream) {
     if (n < 0 || !state) return fail(TPL_EINVAL, "tpl_afterstates: null state");
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_afterstates: plane_stride < n");
-    if (!feats && !flags && !feats_f32) return fail(TPL_EINVAL, "tpl_afterstates: no output requested");
+    if (n > (1 << 25)) return fail(TPL_ERANGE, "tpl_afterstates: at most 2^25 envs per call (32-bit output offsets)");
+    if (!feats && !feats_f32) return fail(TPL_EINVAL, "tpl_afterstates: no feature output requested");
+    if (feats_f32 && !flags) return fail(TPL_EINVAL, "tpl_afterstates: the float form needs the flags array");
     if (n == 0) return 0;
     const cudaStream_t s = (cudaStream_t)stream;
-    if (feats_f32 && feats)
-        afterstates_kernel<true, true><<<grid_for(n), THREADS, 0, s>>>((const uint4 *)state, plane_stride, n, (uint32_t *)feats, flags,
-                                                                       (float4 *)feats_f32, L, M);
-    else if (feats_f32)
-        afterstates_kernel<false, true><<<grid_for(n), THREADS, 0, s>>>((const uint4 *)state, plane_stride, n, nullptr, flags,
-                                                                        (float4 *)feats_f32, L, M);
-    else
-        afterstates_kernel<true, false><<<grid_for(n), THREADS, 0, s>>>((const uint4 *)state, plane_stride, n, (uint32_t *)feats, flags,
-                                                                        nullptr, L, M);
+    const uint4 *st = (const uint4 *)state; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
+    const unsigned g = grid_persistent(n, 8);
+    if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     return check_launch("tpl_afterstates");
 }
 

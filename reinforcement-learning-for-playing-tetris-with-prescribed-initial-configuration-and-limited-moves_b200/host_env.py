@@ -130,8 +130,9 @@ class HostBatchedTetris:
         return feats.reshape(4, 10, n, 4).transpose(2, 0, 1, 3), flags.reshape(4, 10, n).transpose(2, 0, 1)
 
     def step_observe(self, rot: np.ndarray, loc: np.ndarray, dlines: np.ndarray, flags: np.ndarray, state: np.ndarray,
-                     feats: np.ndarray, aflags: np.ndarray) -> None:
+                     feats: np.ndarray, aflags: Optional[np.ndarray]) -> None:
         """One host-facing rollout step into caller-provided (ideally pinned) uint8/int8 buffers:
-        H2D actions -> move -> auto-reset finished envs -> afterstates -> D2H."""
+        H2D actions -> move -> auto-reset finished envs -> afterstates -> D2H.  ``aflags=None`` selects the
+        compact form (feats byte 0 = rows cleared | flags << 3)."""
         _lib.check(self._L.tpl_env_step_observe(self._h, _p(rot), _p(loc), _p(dlines), _p(flags), _p(state), _p(feats), _p(aflags)),
                    "tpl_env_step_observe")

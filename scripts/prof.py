@@ -37,7 +37,7 @@ for i in range(tot):
     if i == a.warmup:
         e0.record()
     if a.what == "pipeline":
-        env.afterstates(); env.move(rot[i], loc[i]); env.reset(done_only=True)
+        env.afterstates(packed=True); env.move(rot[i], loc[i]); env.reset(done_only=True)
     elif a.what == "afterstates_f32":
         env.afterstates(f32=True, u8=False); env.move(rot[i], loc[i]); env.reset(done_only=True)
     elif a.what == "rollout_random":
@@ -48,7 +48,7 @@ e1.record()
 torch.cuda.synchronize()
 if a.what == "pipeline":
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    evs[0].record(); env.afterstates(); evs[1].record(); env.move(rot[0], loc[0]); evs[2].record(); env.reset(done_only=True); evs[3].record()
+    evs[0].record(); env.afterstates(packed=True); evs[1].record(); env.move(rot[0], loc[0]); evs[2].record(); env.reset(done_only=True); evs[3].record()
     torch.cuda.synchronize()
     print("  kernels ms: afterstates %.4f step %.4f reset %.4f" % tuple(evs[j].elapsed_time(evs[j + 1]) for j in range(3)))
 print(f"{a.what}: {e0.elapsed_time(e1) / a.steps:.4f} ms per pass, launches={tp.launch_count()}")

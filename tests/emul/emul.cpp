@@ -16,7 +16,7 @@ struct HostSink {
     uint32_t *feats; uint8_t *flags; float *ff; size_t n, i;
     void put(int slot, uint32_t word, uint32_t fl) {
         const size_t o = (size_t)slot * n + i;
-        if (feats) feats[o] = word;
+        if (feats) feats[o] = flags ? word : (word | (fl << 3));      // no flags array: pack them into byte 0
         if (flags) flags[o] = (uint8_t)fl;
         if (ff) { ff[4 * o] = (float)(word & 0xFF); ff[4 * o + 1] = (float)((word >> 8) & 0xFF);
                   ff[4 * o + 2] = (float)((word >> 16) & 0xFF); ff[4 * o + 3] = (float)(word >> 24); }

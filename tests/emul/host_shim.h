@@ -25,5 +25,31 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31u));
 }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(v >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline uint32_t __vsadu4(uint32_t a, uint32_t b) {
+    uint32_t s = 0;
+    for (int i = 0; i < 4; ++i) { int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF; s += (uint32_t)(x > y ? x - y : y - x); }
+    return s;
+}
+static inline uint32_t __sad(int a, int b, uint32_t c) { return c + (uint32_t)(a > b ? a - b : b - a); }
+static inline uint32_t __viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        const int16_t x = (int16_t)(a >> (16 * i)), y = (int16_t)(b >> (16 * i)), z = (int16_t)(c >> (16 * i));
+        const int16_t sum = (int16_t)(x + y);
+        r |= (uint32_t)(uint16_t)(sum > z ? sum : z) << (16 * i);
+    }
+    return r;
+}
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }

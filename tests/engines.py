@@ -108,6 +108,11 @@ class EmulEngine:
         out = (feats.reshape(4, 10, n, 4).transpose(2, 0, 1, 3), flags.reshape(4, 10, n).transpose(2, 0, 1))
         return out + (ff.reshape(4, 10, n, 4).transpose(2, 0, 1, 3),) if f32 else out
 
+    def afterstates_packed(self, s, L, M):
+        feats = np.zeros((40, s.n, 4), np.uint8)
+        self.L.emul_afterstates(_np_ptr(s.planes), s.stride, s.n, _np_ptr(feats), None, None, L, M)
+        return feats.reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
+
     def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
         idx = self._c(idx, np.int32); mask = self._c(mask, np.uint8)
         self.L.emul_reset_from_pool(_np_ptr(s.planes), s.stride, s.n, _np_ptr(pool), pool.shape[0], _np_ptr(idx), _np_ptr(mask),
@@ -224,6 +229,13 @@ class GpuEngine:
                                          self._stream()), "tpl_afterstates")
         out = (feats.cpu().numpy().reshape(4, 10, n, 4).transpose(2, 0, 1, 3), flags.cpu().numpy().reshape(4, 10, n).transpose(2, 0, 1))
         return out + (ff.cpu().numpy().reshape(4, 10, n, 4).transpose(2, 0, 1, 3),) if f32 else out
+
+    def afterstates_packed(self, s, L, M):
+        t = self.torch
+        feats = t.zeros((40, s.n, 4), dtype=t.uint8, device=self.dev)
+        self._chk(self.L.tpl_afterstates(self._p(s.planes), s.stride, s.n, self._p(feats), None, None, L, M, self._stream()),
+                  "tpl_afterstates(packed)")
+        return feats.cpu().numpy().reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
 
     def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
         d_idx, d_mask = self._t(idx, np.int32), self._t(mask, np.uint8)

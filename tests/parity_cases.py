@@ -197,6 +197,9 @@ def case_afterstates_vs_oracle(eng, n, L, M, seed, pre_moves=3):
     assert np.array_equal(flags.reshape(n, 40), ofl)
     assert np.array_equal(ff.reshape(n, 40, 4), of.astype(np.float32))
     assert_same(eng, s, ost, "afterstates must not modify the state")
+    pk = eng.afterstates_packed(s, L, M).reshape(n, 40, 4)            # compact form: byte 0 = dlines | flags << 3
+    exp = of.copy(); exp[:, :, 0] |= (ofl << 3)
+    assert np.array_equal(pk, exp)
     return of, ofl
 
 
