@@ -27,6 +27,11 @@ L_LINES, M_MOVES = 10, 30
 SEED = 0
 ALG_BYTES_AFTERSTATES = 64 + 40 * 4           # read one 64 B record, write 40 x 4 B (features with the flags packed in byte 0)
 ALG_BYTES_STEP = 64 + 2 + 64 + 3              # record in, action in, record out, (dlines, flags, state) out
+# dram__bytes_read.sum + dram__bytes_write.sum of one afterstates_kernel<0> launch at 2^20 envs, from the ncu --set full
+# capture summarised in profiles/r01_ncu_full_v2_afterstates.txt (67.2 MB + 112.7 MB; the rest of the 160 MiB of
+# output is still in L2 when the kernel ends)
+NCU_TRAFFIC_AFTERSTATES_2P20 = 179.9e6
+NCU_ALU_PIPE_PCT = 79.4                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, same capture
 
 
 def load_peaks():
@@ -70,7 +75,7 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as e:          # NVML missing: report it, do not fail the bench
             self.err = repr(e)
 
@@ -221,11 +226,11 @@ def run_b200(args):
         env.reset(done_only=True)
         if ev: ev[3].record()
 
+    sampler = ClockSampler(local); sampler.start()     # samples through warm-up, the timed region and the e2e leg
     for i in range(W):
         one_step(i)
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     launches0 = tp.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -239,7 +244,6 @@ def run_b200(args):
     t_end.record()
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    sampler.stop_flag = True; sampler.join(timeout=2)
     launches = tp.launch_count() - launches0
     ms = torch.tensor([t_start.elapsed_time(t_end)], device=dev, dtype=torch.float64)
     if dist: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -265,6 +269,7 @@ def run_b200(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if dist: dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+    sampler.stop_flag = True; sampler.join(timeout=2)
     henv.close()
 
     if rank != 0:
@@ -281,7 +286,9 @@ def run_b200(args):
         "config": workload_config(args, n_total),
         "env_steps_per_sec": n_total * K / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "kernel": "afterstates_kernel", "achieved": as_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": as_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": as_gbs / hbm_peak, "traffic": NCU_TRAFFIC_AFTERSTATES_2P20 if n == (1 << 20) else None,
+                     "peak_source": peak_src, "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT,
+                                                                "note": "kernel is ALU-pipe-bound, not HBM-bound (DESIGN.md section 3)"},
                      "algorithmic_bytes_per_launch": ALG_BYTES_AFTERSTATES * n, "avg_launch_ms": k_ms[0]},
         "kernels": {
             "afterstates": {"ms": k_ms[0], "afterstates_per_s": n * 40 / (k_ms[0] * 1e-3), "GBps": as_gbs},
@@ -350,7 +357,7 @@ def extra_single_gpu(tp, torch, dev, pool, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)

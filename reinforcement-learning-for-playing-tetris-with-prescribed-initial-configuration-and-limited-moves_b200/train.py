@@ -1,0 +1,183 @@
+"""DQN afterstate-value training loop driving the batched GPU envs (BASELINE config 4: 65 536 envs).
+
+The reference's ``model/train.py`` stops after building the network and the optimiser (``:25-27``); this is that
+loop completed with the reference's own hyper-parameters (``model/train.py:15-21``), the optimiser it names
+(``AdamW(lr=LR, amsgrad=True)``, ``:27``) and the standard DQN pieces those constants imply (replay memory,
+exponentially decaying epsilon-greedy, Huber loss, soft target update with TAU).
+
+Afterstate formulation: the action value of placing the current piece at slot (rot, loc) is
+``r(slot) + GAMMA * V(afterstate(slot))``; ``V`` is ``ValueNet`` on the four features the env kernel emits.
+Everything stays on the GPU: env state, the 40-slot enumeration (``tpl_afterstates``), the chosen move
+(``tpl_step``), auto-reset (``tpl_reset_from_pool``), the replay memory and the network.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from .batched import FLAG_ALIAS, FLAG_LOSE, FLAG_NOPIECE, FLAG_TOPOUT, FLAG_WIN, BatchedTetris
+from .configs import ConfigPool, synthetic_pool
+from .model import ValueNet
+
+# the reference's constants, model/train.py:15-21
+BATCH_SIZE = 128
+GAMMA = 0.99
+EPS_START = 0.9
+EPS_END = 0.05
+EPS_DECAY = 1000
+TAU = 0.005
+LR = 1e-4
+
+
+def reward_from(dlines: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """Reward as a pure function of the pinned integers the env reports: rows cleared by the move, +10 for
+    reaching L lines, -10 for topping out or running out of moves (the reference has no reward)."""
+    r = dlines.to(torch.float32)
+    r = r + 10.0 * ((flags & FLAG_WIN) != 0).to(torch.float32)
+    r = r - 10.0 * ((flags & (FLAG_LOSE | FLAG_TOPOUT)) != 0).to(torch.float32)
+    return r
+
+
+class ReplayMemory:
+    """Ring buffer on the device: chosen afterstate (4 x u8), reward, done, and the next state's 40 afterstates
+    (features + flags, u8) for the max in the TD target."""
+
+    def __init__(self, capacity: int, device):
+        self.capacity, self.size, self.pos = capacity, 0, 0
+        self.x = torch.zeros((capacity, 4), dtype=torch.uint8, device=device)
+        self.r = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self.done = torch.zeros(capacity, dtype=torch.bool, device=device)
+        self.nx = torch.zeros((capacity, 40, 4), dtype=torch.uint8, device=device)
+        self.nfl = torch.zeros((capacity, 40), dtype=torch.uint8, device=device)
+
+    def push(self, x, r, done, nx, nfl):
+        n = x.shape[0]
+        if n > self.capacity:
+            x, r, done, nx, nfl = x[:self.capacity], r[:self.capacity], done[:self.capacity], nx[:self.capacity], nfl[:self.capacity]
+            n = self.capacity
+        idx = (torch.arange(n, device=x.device) + self.pos) % self.capacity
+        self.x[idx], self.r[idx], self.done[idx], self.nx[idx], self.nfl[idx] = x, r, done, nx, nfl
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch: int, gen):
+        idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
+        return self.x[idx], self.r[idx], self.done[idx], self.nx[idx], self.nfl[idx]
+
+
+@dataclass
+class TrainStats:
+    env_steps: int = 0
+    optim_steps: int = 0
+    loss: float = float("nan")
+    eps: float = EPS_START
+    env_seconds: float = 0.0
+    total_seconds: float = 0.0
+    episodes: int = 0
+    wins: int = 0
+
+    @property
+    def env_steps_per_s(self):
+        return self.env_steps / max(self.env_seconds, 1e-9)
+
+    @property
+    def e2e_steps_per_s(self):
+        return self.env_steps / max(self.total_seconds, 1e-9)
+
+
+def select_slots(values: torch.Tensor, flags: torch.Tensor, eps: float, gen) -> torch.Tensor:
+    """Epsilon-greedy over the distinct placements: values/flags are [40, N]; alias / no-piece slots are never
+    chosen.  Returns the slot index int64[N]."""
+    invalid = (flags & (FLAG_ALIAS | FLAG_NOPIECE)) != 0
+    greedy = values.masked_fill(invalid, float("-inf")).argmax(dim=0)
+    noise = torch.rand(values.shape, device=values.device, generator=gen).masked_fill(invalid, -1.0)
+    explore = torch.rand(values.shape[1], device=values.device, generator=gen) < eps
+    return torch.where(explore, noise.argmax(dim=0), greedy)
+
+
+def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
+          config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
+          batch_size: int = BATCH_SIZE, log_every: int = 0) -> tuple:
+    """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
+    Returns (policy_net, TrainStats)."""
+    dev = torch.device(device)
+    pool = config_pool if config_pool is not None else synthetic_pool(4096, seed=seed, M=M)
+    env = BatchedTetris(num_envs, L, M, device=dev, seed=seed, config_pool=pool)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    torch.manual_seed(seed)
+    policy_net = ValueNet().to(dev)
+    target_net = ValueNet().to(dev)
+    target_net.load_state_dict(policy_net.state_dict())
+    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True)          # model/train.py:27
+    loss_fn = nn.SmoothL1Loss()
+    memory = ReplayMemory(replay_capacity, dev)
+    st = TrainStats()
+    ar = torch.arange(num_envs, device=dev)
+    t_all = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env_ms = 0.0
+
+    feats, flags, ff = env.afterstates(f32=True)           # [N,4,10,4] u8 view, [N,4,10] view, [40N,4] f32
+    for it in range(iterations):
+        eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
+        with torch.no_grad():
+            values = policy_net(ff).view(40, num_envs)
+            fl40 = flags.permute(1, 2, 0).reshape(40, num_envs)
+            r_slot = reward_from(feats[..., 0].permute(1, 2, 0).reshape(40, num_envs), fl40)
+            slot = select_slots(r_slot + GAMMA * values, fl40, eps, gen)
+        rot, loc = (slot // 10).to(torch.uint8), (slot % 10).to(torch.uint8)
+        x = feats.reshape(num_envs, 40, 4)[ar, slot].clone()                        # chosen afterstate features
+        ev0.record()
+        dlines, mflags, state = env.move(rot, loc)
+        reward = reward_from(dlines, mflags)
+        done = state != 0
+        env.reset(done_only=True)
+        feats, flags, ff = env.afterstates(f32=True)
+        ev1.record()
+        memory.push(x, reward, done, feats.reshape(num_envs, 40, 4), flags.reshape(num_envs, 40))
+        st.env_steps += num_envs
+        if memory.size >= batch_size:
+            for _ in range(optim_steps_per_iter):
+                bx, br, bdone, bnx, bnfl = memory.sample(batch_size, gen)
+                with torch.no_grad():
+                    nv = target_net(bnx.view(-1, 4)).view(batch_size, 40)
+                    nr = reward_from(bnx[..., 0], bnfl)
+                    q = (nr + GAMMA * nv * ((bnfl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
+                        (bnfl & (FLAG_ALIAS | FLAG_NOPIECE)) != 0, float("-inf"))
+                    best_next = q.max(dim=1).values
+                    # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal)
+                    target = torch.where(bdone, torch.zeros_like(best_next), best_next)
+                loss = loss_fn(policy_net(bx), target)
+                optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                torch.nn.utils.clip_grad_value_(policy_net.parameters(), 100)
+                optimizer.step()
+                with torch.no_grad():                                               # soft update, TAU
+                    for tp_, pp in zip(target_net.parameters(), policy_net.parameters()):
+                        tp_.mul_(1 - TAU).add_(pp, alpha=TAU)
+                st.optim_steps += 1
+            st.loss = float(loss.item())
+        torch.cuda.synchronize(dev)
+        env_ms += ev0.elapsed_time(ev1)
+        st.eps = eps
+        if log_every and (it + 1) % log_every == 0:
+            s = env.reduce_stats()
+            print(f"it {it + 1}: eps {eps:.3f} loss {st.loss:.4f} episodes {s['episodes']} wins {s['wins']} "
+                  f"lines/episode {s['lines'] / max(s['episodes'], 1):.2f}")
+    st.env_seconds = env_ms * 1e-3
+    st.total_seconds = time.perf_counter() - t_all
+    s = env.reduce_stats()
+    st.episodes, st.wins = s["episodes"], s["wins"]
+    return policy_net, st
+
+
+if __name__ == "__main__":
+    net, stats = train(log_every=20)
+    print(stats, f"env-only {stats.env_steps_per_s:.3e} steps/s, end-to-end {stats.e2e_steps_per_s:.3e} steps/s")

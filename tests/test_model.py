@@ -1,0 +1,44 @@
+"""The PyTorch side (value net + DQN loop): CPU checks of the network, GPU smoke of the loop."""
+import pytest
+import torch
+
+
+def _mod(name):
+    import tetris_piclim as tp
+    from importlib import import_module
+    return import_module(tp.__name__ + "." + name)
+
+
+def test_model_matches_reference_layer_shape():
+    m = _mod("model")
+    net = m.Model(217, 14)                                  # the shapes model/train.py:26 asks for
+    shapes = [tuple(p.shape) for p in net.parameters()]
+    assert shapes == [(128, 217), (128,), (128, 128), (128,), (128, 128), (128,), (128, 128), (128,), (14, 128), (14,)]
+    assert net(torch.zeros(3, 217)).shape == (3, 14)
+    v = m.ValueNet()
+    assert v(torch.zeros(5, 4, dtype=torch.uint8)).shape == (5,)
+
+
+def test_hyperparameters_are_the_reference_ones():
+    t = _mod("train")
+    assert (t.BATCH_SIZE, t.GAMMA, t.EPS_START, t.EPS_END, t.EPS_DECAY, t.TAU, t.LR) == (128, 0.99, 0.9, 0.05, 1000, 0.005, 1e-4)
+
+
+def test_select_slots_never_picks_alias():
+    t = _mod("train")
+    g = torch.Generator(); g.manual_seed(0)
+    values = torch.randn(40, 64)
+    flags = torch.zeros(40, 64, dtype=torch.uint8)
+    flags[10:] = 8
+    values[10:] = 100.0
+    for eps in (0.0, 0.5, 1.0):
+        s = t.select_slots(values, flags, eps, g)
+        assert int(s.max()) < 10
+
+
+@pytest.mark.gpu
+def test_dqn_loop_runs_on_gpu(gpu):
+    t = _mod("train")
+    net, st = t.train(num_envs=4096, iterations=12, optim_steps_per_iter=2)
+    assert st.env_steps == 4096 * 12 and st.optim_steps == 24
+    assert st.loss == st.loss and st.episodes > 0            # finite loss, episodes finished and were reset
