@@ -2,8 +2,10 @@
 """bench.py -- headline benchmark of the Tetris-piclim hot path on B200 (contract: see DESIGN.md "Measurement").
 
 One "step" = one pass of the hot path over one batch of envs, exactly what a rollout does between two value-net
-calls:   tpl_afterstates (40 slots + features per env, written to HBM)  ->  tpl_step (Tetris.move with the chosen
-action)  ->  tpl_reset_from_pool (auto-reset of finished episodes from the prescribed-config pool).
+calls:   Tetris.move with the chosen action  ->  auto-reset of finished episodes from the prescribed-config pool  ->
+40-slot afterstate enumeration + features of the new state, written to HBM.  It is ONE kernel launch
+(tpl_step_observe); the three stand-alone kernels it fuses (tpl_step, tpl_reset_from_pool, tpl_afterstates) are timed
+separately after the timed region and reported under "kernels".
 Workload at N GPUs: 2^20 envs per GPU (BASELINE.json configs[2] at N=1, configs[4] = 8M envs at N=8), L=10, M=30,
 pool = 4096 synthetic prescribed boards + the 256 carve-generated configs of tests/golden; weak scaling, envs sharded
 by global env id, one NCCL all-reduce of the 64-byte episode-stats vector per rollout.
@@ -27,10 +29,12 @@ L_LINES, M_MOVES = 10, 30
 SEED = 0
 ALG_BYTES_AFTERSTATES = 64 + 40 * 4           # read one 64 B record, write 40 x 4 B (features with the flags packed in byte 0)
 ALG_BYTES_STEP = 64 + 2 + 64 + 3              # record in, action in, record out, (dlines, flags, state) out
+ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out once, action, results, 40 packed feature words
 # dram__bytes_read.sum + dram__bytes_write.sum of one afterstates_kernel<0> launch at 2^20 envs, from the ncu --set full
 # capture summarised in profiles/r01_ncu_full_v2_afterstates.txt (67.2 MB + 112.7 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
 NCU_TRAFFIC_AFTERSTATES_2P20 = 179.9e6
+NCU_TRAFFIC_FUSED_2P20 = None                 # filled from the fused kernel's capture (profiles/)
 NCU_ALU_PIPE_PCT = 79.4                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, same capture
 
 
@@ -218,27 +222,20 @@ def run_b200(args):
     rot = torch.randint(0, 4, (total, n), device=dev, dtype=torch.uint8, generator=g)
     loc = torch.randint(0, 10, (total, n), device=dev, dtype=torch.uint8, generator=g)
 
-    def one_step(i, ev=None):
-        env.afterstates(packed=True)
-        if ev: ev[1].record()
-        env.move(rot[i], loc[i])
-        if ev: ev[2].record()
-        env.reset(done_only=True)
-        if ev: ev[3].record()
+    def one_step(i):
+        env.step_observe(rot[i], loc[i], packed=True)          # ONE launch: move -> auto-reset -> afterstates
 
     sampler = ClockSampler(local); sampler.start()     # samples through warm-up, the timed region and the e2e leg
     for i in range(W):
         one_step(i)
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     launches0 = tp.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
     for i in range(K):
-        evs[i][0].record()
-        one_step(W + i, evs[i])
+        one_step(W + i)
     stats = env.stats.clone()
     if dist: dist.all_reduce(stats)            # the one collective of the path: 64 bytes per rollout
     t_end.record()
@@ -248,7 +245,17 @@ def run_b200(args):
     ms = torch.tensor([t_start.elapsed_time(t_end)], device=dev, dtype=torch.float64)
     if dist: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    k_ms = [sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K for j in range(3)]
+
+    # the three stand-alone kernels the fused step replaces, CUDA-event timed one by one (explanatory numbers)
+    ksteps = min(K, 20)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(ksteps)]
+    for i in range(ksteps):
+        evs[i][0].record(); env.afterstates(packed=True)
+        evs[i][1].record(); env.move(rot[i], loc[i])
+        evs[i][2].record(); env.reset(done_only=True)
+        evs[i][3].record()
+    torch.cuda.synchronize()
+    k_ms = [sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(ksteps)) / ksteps for j in range(3)]
 
     # ---- end-to-end through the host-buffer C ABI (pinned host buffers, H2D + D2H inside the timed region) ----
     henv = tp.HostBatchedTetris(n, L_LINES, M_MOVES, device=local, seed=SEED, env_base=rank * n, config_pool=pool)
@@ -279,19 +286,24 @@ def run_b200(args):
     n_total = n * world
     hbm_peak, peak_src = load_peaks()
     as_gbs = ALG_BYTES_AFTERSTATES * n / (k_ms[0] * 1e-3) / 1e9
+    fused_ms = ms_total / K
+    fused_gbs = ALG_BYTES_FUSED * n / (fused_ms * 1e-3) / 1e9
     line = {
         "metric": "afterstates/sec", "value": n_total * 40 * K / (ms_total * 1e-3), "unit": "afterstates/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, n_total),
         "env_steps_per_sec": n_total * K / (ms_total * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": "afterstates_kernel", "achieved": as_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": as_gbs / hbm_peak, "traffic": NCU_TRAFFIC_AFTERSTATES_2P20 if n == (1 << 20) else None,
-                     "peak_source": peak_src, "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT,
-                                                                "note": "kernel is ALU-pipe-bound, not HBM-bound (DESIGN.md section 3)"},
-                     "algorithmic_bytes_per_launch": ALG_BYTES_AFTERSTATES * n, "avg_launch_ms": k_ms[0]},
+        "roofline": {"bound": "hbm", "kernel": "step_observe_kernel<0> (fused move + auto-reset + afterstates)",
+                     "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
+                     "traffic": NCU_TRAFFIC_FUSED_2P20 if n == (1 << 20) else None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_FUSED * n, "avg_launch_ms": fused_ms,
+                     "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT,
+                                      "note": "the kernel is ALU-pipe-bound, not HBM-bound (DESIGN.md section 3)"}},
         "kernels": {
-            "afterstates": {"ms": k_ms[0], "afterstates_per_s": n * 40 / (k_ms[0] * 1e-3), "GBps": as_gbs},
+            "note": "stand-alone kernels (3 launches per step); their sum is what the fused step replaces",
+            "afterstates": {"ms": k_ms[0], "afterstates_per_s": n * 40 / (k_ms[0] * 1e-3), "GBps": as_gbs,
+                            "frac_of_hbm_peak": as_gbs / hbm_peak},
             "step": {"ms": k_ms[1], "env_steps_per_s": n / (k_ms[1] * 1e-3), "GBps": ALG_BYTES_STEP * n / (k_ms[1] * 1e-3) / 1e9},
             "reset_done": {"ms": k_ms[2]},
         },

@@ -118,6 +118,14 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
 int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *feats, uint8_t *flags,
                     float *feats_f32, int L, int M, void *stream);
 
+/* The fused hot-path step: tpl_step, then tpl_reset_from_pool(TPL_RESET_DONE) (skipped when pool == NULL), then
+ * tpl_afterstates of the resulting state, in ONE kernel: each record is read once and written once.  Arguments as in
+ * the three calls it replaces; results are identical to running them in sequence. */
+int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc,
+                     int8_t *dlines, uint8_t *flags, int8_t *st, long long *stats,
+                     const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
+                     uint8_t *feats, uint8_t *aflags, float *feats_f32, int L, int M, void *stream);
+
 /* Counter-based 7-bag piece sequences (contract of RandomPieceGenerator.get_random_sequence, :95-102):
  * out u8[n][count]; episode u32[n] or NULL (= episode0 for all). */
 int tpl_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode,

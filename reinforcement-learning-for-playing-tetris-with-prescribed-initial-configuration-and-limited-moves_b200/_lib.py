@@ -20,6 +20,7 @@ DEVICE_API = {
     "reset_from_pool": (c_int, [P, c_int64, c_int, P, c_int, P, P, c_int, P, c_uint64, c_uint64, c_int, P]),
     "step": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, c_int, c_int, P]),
     "afterstates": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P]),
+    "step_observe": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, c_uint64, c_uint64, c_int, P, P, P, c_int, c_int, P]),
     "gen_pieces": (c_int, [P, c_int, c_int, c_uint64, c_uint64, P, c_uint32, P]),
     "rollout_random": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int, c_int, c_int, P]),
     "rollout_greedy": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, P, c_uint64, c_uint64, c_int, c_int, c_int, P]),

@@ -235,6 +235,29 @@ class BatchedTetris:
         gv = flags.view(4, 10, n).permute(2, 0, 1) if flags is not None else None
         return (fv, gv, ff) if f32 else (fv, gv)
 
+    # ------------------------------------------------------------------ fused hot-path step
+    def step_observe(self, rot, loc, packed: bool = True, f32: bool = False, auto_reset: bool = True):
+        """move -> auto-reset of finished envs -> afterstates of the resulting state, in ONE kernel launch
+        (``tpl_step_observe``): the rollout inner loop between two value-net calls.  ``rot``/``loc`` must be uint8
+        CUDA tensors [N].  Returns (rows cleared, move flags, state after the move, feats, afterstate flags or None,
+        feats_f32 or None); ``feats`` is the raw slot-major uint8 [40, N, 4] buffer (compact form when ``packed``)."""
+        n = self.num_envs
+        if auto_reset:
+            self._need_pool()
+        if packed and f32:
+            raise ValueError("the packed form has no float output")
+        d_rot, d_loc = self._dev(rot, torch.uint8, (n,)), self._dev(loc, torch.uint8, (n,))
+        dl, fl, st = self._buf("dlines", (n,), torch.int8), self._buf("mflags", (n,), torch.uint8), self._buf("mstate", (n,), torch.int8)
+        feats = self._buf("feats", (40, n, 4), torch.uint8) if not (f32 and not packed and False) else None
+        aflags = None if packed else self._buf("aflags", (40, n), torch.uint8)
+        ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
+        _lib.check(self._L.tpl_step_observe(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
+                                            _ptr(self.stats) if self.count_stats else None,
+                                            _ptr(self.pool) if auto_reset else None, self.pool_size, _ptr(self.episode), self.seed,
+                                            self.env_base, self.gen_pieces, _ptr(feats), _ptr(aflags), _ptr(ff), self.L, self.M,
+                                            self._stream()), "tpl_step_observe")
+        return dl, fl, st, feats, aflags, ff
+
     # ------------------------------------------------------------------ fused rollouts
     def _need_pool(self):
         if self.pool is None:

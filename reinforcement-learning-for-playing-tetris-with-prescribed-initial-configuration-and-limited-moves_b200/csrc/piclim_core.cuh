@@ -173,26 +173,44 @@ __device__ __forceinline__ uint32_t mul_fma_pipe(uint32_t a, uint32_t b) {
 // ---------------------------------------------------------------------------------------------
 struct MoveOut { int k; bool topout; };
 
-__device__ __forceinline__ MoveOut place_general(uint32_t (&x)[COLS], const uint4 &o, const uint4 &ob, int loc_raw) {
-    const int w = orient_w(o), h = orient_h(o);
+// Per-thread scratch for the one place where a column index is data-dependent (the move's location):
+// SCR_ROWS words per thread at scr[k * ss]; with ss = blockDim.x the words of a warp sit in 32 different
+// banks, so the dynamic accesses are conflict-free.  Rows 10..12 are padding for loc + j > 9.
+constexpr int SCR_ROWS = 13;
+
+// v >> s with s >= 32 giving 0 (PTX shift semantics; `>>` in C++ is undefined there)
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t s) {
+#ifdef TPL_HOST_EMUL
+    return s >= 32 ? 0u : v >> s;
+#else
+    return __funnelshift_rc(v, 0u, s);
+#endif
+}
+
+// The move on bit-columns for a run-time location.  Hard drop (:424-433) in one bit-scan:
+//   max_j(H[loc+j] - bo_j) = bfind( OR_j (col[loc+j] >> bo_j) ) + 1
+// (bo_j = 64 for the columns the shape does not cover, which shifts them out entirely).
+__device__ __forceinline__ MoveOut place_general(uint32_t (&x)[COLS], uint32_t *scr, int ss, const uint4 &o, const uint4 &ob,
+                                                 int loc_raw) {
+    const int w = orient_w(o);
     const int loc = min(loc_raw, COLS - w);                                  // :364
-    // align the piece's 4-bit column images / bottom offsets with the board columns
-    const uint64_t PB = (uint64_t)(o.x & 0xFFFFu) << (4 * loc);
-    const uint64_t BO = (uint64_t)(ob.x & 0xFFFFu) << (4 * loc);
-    uint32_t pk[COLS];
-    int y = 0;
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) {
-        pk[k] = (uint32_t)(PB >> (4 * k)) & 15u;
-        const int bo = (int)((uint32_t)(BO >> (4 * k)) & 15u);
-        const int d = col_height(x[k]) - bo;                                 // :427-433 in height form
-        y = pk[k] ? max(y, d) : y;
-    }
-    MoveOut r; r.k = 0; r.topout = (y + h > ROWS);                            // drop = 20 - h - y < 0
+    for (int k = 0; k < COLS; ++k) scr[k * ss] = x[k];
+    uint32_t *win = scr + loc * ss;
+    const uint32_t v0 = win[0], v1 = win[ss], v2 = win[2 * ss], v3 = win[3 * ss];
+    const uint32_t t = shr_clamp(v0, o.y & 0xFFu) | shr_clamp(v1, (o.y >> 8) & 0xFFu) | shr_clamp(v2, (o.y >> 16) & 0xFFu) |
+                       shr_clamp(v3, o.y >> 24);
+    const int y = col_height(t);
+    MoveOut r; r.k = 0; r.topout = (y > (int)ob.z);                           // drop = 20 - h - y < 0  (:372-374)
     if (r.topout) return r;
-    uint32_t full = ((1u << h) - 1u) << y;                                    // only the piece's rows (:382-383)
+    const uint32_t pw = 1u << y;
+    win[0] = v0 | ((o.x & 15u) * pw);                                         // :377-378
+    win[ss] = v1 | (((o.x >> 4) & 15u) * pw);
+    win[2 * ss] = v2 | (((o.x >> 8) & 15u) * pw);
+    win[3 * ss] = v3 | (((o.x >> 12) & 15u) * pw);
+    uint32_t full = ob.y * pw;                                                // only the piece's rows (:382-383)
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) { x[k] |= pk[k] << y; full &= x[k]; }      // :377-378
+    for (int k = 0; k < COLS; ++k) { x[k] = scr[k * ss]; full &= x[k]; }
     r.k = __popc(full);
     while (full) {                                                            // :397-407, highest row first
         const int q = 31 - __clz(full);

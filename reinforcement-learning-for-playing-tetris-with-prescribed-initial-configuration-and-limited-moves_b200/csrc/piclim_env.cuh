@@ -52,14 +52,14 @@ __device__ __forceinline__ void install_config(Env &e, const uint4 *__restrict__
 // step: Tetris.move (game/tetris.py:354-422).  Returns the TPL_FLAG_* bits; k = rows cleared.
 // tab: 28 entries x 2 uint4 (see piclim_core.cuh)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t rot, uint32_t loc, int L, int M, int &k,
-                                             bool &board_changed) {
+__device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t *scr, int ss, uint32_t rot, uint32_t loc, int L, int M,
+                                             int &k, bool &board_changed) {
     k = 0; board_changed = false;
     if (e.head >= e.npieces) return F_NOPIECE;
     const uint32_t piece = queue_piece(e.q, e.head);                        // :356 pop(0)
     e.head += 1;
     const uint32_t t = (piece * 4 + (rot & 3u)) * 2;                        // :359 / :61
-    const MoveOut m = place_general(e.col, tab[t], tab[t + 1], (int)loc);
+    const MoveOut m = place_general(e.col, scr, ss, tab[t], tab[t + 1], (int)loc);
     k = m.k; board_changed = !m.topout;
     return apply_outcome(e, m, L, M);
 }
@@ -102,7 +102,12 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           uint32_t flN, uint32_t flT, bool canon, int w,
                                           int bo0, int bo1, int bo2, int bo3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO01, uint32_t TO23, uint32_t hm, int thr,
-                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask) {
+                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, int cmax_warp) {
+    if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
+        fl |= F_ALIAS;
+        if (!pend) sink.put(r * 10 + C, word, fl);
+        return;
+    }
     const int y = max(max(H[C] - bo0, H[C + 1] - bo1), max(H[C + 2] - bo2, H[C + 3] - bo3));
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
@@ -131,13 +136,21 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     if (!pend) sink.put(r * 10 + C, word, fl);
 }
 
-template <class Sink>
-__device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, int L, int M, Sink &sink) {
-    if (e.head >= e.npieces) {
+// UNIFORM = true is the variant for warps whose lanes were sorted by piece (afterstates_sorted_kernel): every lane of
+// the warp must call it (no early exit), rotations that are aliases for every lane (r >= max n_rot in the warp) and
+// columns no lane can reach (c > max(10 - w)) are not enumerated but copied from the slot they alias -- on average
+// 23 of the 40 slots are distinct placements.  Needs a sink with copy(dst, src, extra_flags).
+template <bool UNIFORM, class Sink>
+__device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink) {
+    const bool nopiece = e.head >= e.npieces;
+    if (!UNIFORM && nopiece) {
         for (int s = 0; s < 40; ++s) sink.put(s, 0u, F_NOPIECE);
         return;
     }
-    const uint32_t piece = queue_piece(e.q, e.head);
+    // a lane without a piece walks through as an O piece (its stores are overwritten at the end)
+    const uint32_t piece = nopiece ? 6u : queue_piece(e.q, e.head);
+    int nrot_warp = 4;
+    if constexpr (UNIFORM) nrot_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)orient_nrot(tab[piece * 8]));
 
     // ---- per-env precompute, shared by all 40 slots.  Indices 10..13 are neutral padding (full columns for
     //      the AND, height 0); every use of them in a pair sum is statically excluded.
@@ -178,9 +191,11 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
     unsigned long long pending = 0ull;
 
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < nrot_warp; ++r) {
         const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
         const int w = orient_w(o);
+        int cmax_warp = 9;
+        if constexpr (UNIFORM) cmax_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(COLS - w));
         const int bo0 = o.y & 0xFF, bo1 = (o.y >> 8) & 0xFF, bo2 = (o.y >> 16) & 0xFF, bo3 = o.y >> 24;
         const uint32_t cb0 = o.x & 15u, cb1 = (o.x >> 4) & 15u, cb2 = (o.x >> 8) & 15u, cb3 = (o.x >> 12) & 15u;
         const uint32_t afl = orient_alias(o) ? F_ALIAS : 0u;
@@ -188,7 +203,7 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
         uint32_t word = 0, fl = 0, pmask = 0; bool pend = false;
 #define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, K, U, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
-                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask);
+                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         pending |= (unsigned long long)pmask << (10 * r);
@@ -203,7 +218,7 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
         uint32_t x[COLS];
 #pragma unroll
         for (int k = 0; k < COLS; ++k) x[k] = e.col[k];
-        const MoveOut m = place_general(x, o, ob, c);
+        const MoveOut m = place_general(x, scr, ss, o, ob, c);
         const uint32_t f3 = board_features(x, (int)cells + 4 - 10 * m.k);
         const uint32_t word = (uint32_t)m.k | (f3 << 8);
         const uint32_t fl = m.k == 0 ? fl_noclear : (((int)e.lines + m.k >= L) ? F_WIN : fl_noclear);   // :389-391, :415-422
@@ -213,6 +228,20 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
             for (int c2 = c; c2 <= cend; ++c2)
                 sink.put(r2 * 10 + c2, word, fl | ((r2 != r || c2 != c) ? F_ALIAS : 0u));
     }
+
+    if constexpr (UNIFORM) {
+        // rotations >= nrot_warp are aliases for every lane (:61): copy them from rot % n_rot (after the deferred slots)
+        const int nrot = orient_nrot(tab[piece * 8]);
+        for (int r = nrot_warp; r < 4; ++r)
+            for (int c = 0; c < COLS; ++c) sink.copy(r * 10 + c, (r % nrot) * 10 + c, F_ALIAS);
+        if (nopiece)
+            for (int s = 0; s < 40; ++s) sink.put(s, 0u, F_NOPIECE);
+    }
+}
+
+template <class Sink>
+__device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink) {
+    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,7 +249,7 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
 //   acc[8] += {episodes, wins, top-outs, move-limit losses, lines, moves placed, steps, resets}
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
-                                                    const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
+                                                    uint32_t *scr, int ss, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
                                                     int gen_count, int L, int M) {
     if (e.state != S_RUNNING || e.head >= e.npieces) {
         ep += 1; t = 0; acc[7] += 1;
@@ -229,7 +258,7 @@ __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32
     const uint4 rw = rng_words(seed, env, ep, STREAM_ACTION, t);
     const uint32_t rot = rw.x & 3u, loc = __umulhi(rw.y, 10u);
     int k; bool changed;
-    const uint32_t fl = step_env(e, tab, rot, loc, L, M, k, changed);
+    const uint32_t fl = step_env(e, tab, scr, ss, rot, loc, L, M, k, changed);
     t += 1;
     acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
     if (e.state != S_RUNNING) {
@@ -258,18 +287,18 @@ struct GreedySink {
 struct GreedyWeights { int w[6]; };
 
 __device__ __forceinline__ void rollout_greedy_step(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
-                                                    const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
+                                                    uint32_t *scr, int ss, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
                                                     int gen_count, int L, int M, const GreedyWeights &gw) {
     if (e.state != S_RUNNING || e.head >= e.npieces) {
         ep += 1; t = 0; acc[7] += 1;
         install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
     }
     GreedySink sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};
-    afterstates_env(e, tab, L, M, sink);
+    afterstates_env(e, tab, scr, ss, L, M, sink);
     const int slot = sink.best_slot < 40 ? sink.best_slot : 0;
     const uint32_t rot = (uint32_t)(slot / 10), loc = (uint32_t)(slot - 10 * (slot / 10));
     int k; bool changed;
-    const uint32_t fl = step_env(e, tab, rot, loc, L, M, k, changed);
+    const uint32_t fl = step_env(e, tab, scr, ss, rot, loc, L, M, k, changed);
     t += 1;
     acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
     if (e.state != S_RUNNING) {

@@ -239,13 +239,16 @@ int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int
     const size_t n = (size_t)e->n;
     CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
-    RC(tpl_step(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->L, e->M, e->stream));
-    RC(tpl_reset_from_pool(e->state, e->stride, e->n, e->pool, e->K, nullptr, nullptr, TPL_RESET_DONE, e->episode, e->seed,
-                           e->env_base, 0, e->stream));
+    if (!feats) return fail(TPL_EINVAL, "tpl_env_step_observe: feats output required");
+    RC(ensure((void **)&e->d_feats, n * 160));
+    if (aflags) RC(ensure((void **)&e->d_aflags, n * 40));
+    RC(tpl_step_observe(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->pool, e->K,
+                        e->episode, e->seed, e->env_base, 0, e->d_feats, aflags ? e->d_aflags : nullptr, nullptr, e->L, e->M, e->stream));
     if (dlines) CU(cudaMemcpyAsync(dlines, e->d_dlines, n, cudaMemcpyDeviceToHost, e->stream));
     if (flags) CU(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, e->stream));
     if (st) CU(cudaMemcpyAsync(st, e->d_st, n, cudaMemcpyDeviceToHost, e->stream));
-    if (feats || aflags) RC(afterstates_to_host(e, feats, aflags));
+    CU(cudaMemcpyAsync(feats, e->d_feats, n * 160, cudaMemcpyDeviceToHost, e->stream));
+    if (aflags) CU(cudaMemcpyAsync(aflags, e->d_aflags, n * 40, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace tpl {
 
@@ -30,6 +31,8 @@ int check_launch(const char *what) {
 }
 long long launches() { return g_launches.load(); }
 const char *last_error() { return g_err; }
+
+#define TPL_SCRATCH __shared__ uint32_t s_scr[SCR_ROWS * THREADS]; uint32_t *scr = s_scr + threadIdx.x
 
 __device__ __forceinline__ void load_table(uint4 *s_tab) {
     if (threadIdx.x < TAB_WORDS4) s_tab[threadIdx.x] = reinterpret_cast<const uint4 *>(c_orient)[threadIdx.x];
@@ -125,13 +128,14 @@ __global__ void __launch_bounds__(THREADS)
 step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
             int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats, int L, int M) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    TPL_SCRATCH;
     load_table(s_tab);
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
         Env e; load_env(st, stride, i, e);
         const uint32_t was = e.state;
         int k; bool changed;
-        const uint32_t fl = step_env(e, s_tab, rot[i], loc[i], L, M, k, changed);
+        const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
         if (changed) {
             st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
             st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
@@ -178,12 +182,187 @@ __global__ void __launch_bounds__(THREADS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    TPL_SCRATCH;
     load_table(s_tab);
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
         Env e; load_env(st, stride, i, e);
         GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n};
-        afterstates_env(e, s_tab, L, M, sink);
+        afterstates_env(e, s_tab, scr, THREADS, L, M, sink);
     }
+}
+
+// =================================================================================================
+// afterstates, piece-sorted tiles (compact output form).
+//
+// The plain kernel above enumerates all 40 slots of every env because the lanes of a warp hold different pieces:
+// rotations >= n_rot and columns > 10 - w are aliases for one lane but real placements for its neighbour.  Here a
+// CTA of 128 threads takes a tile of 256 consecutive envs, counting-sorts their ids by current piece in shared memory
+// (match.any + one shared atomic per warp and piece) and enumerates them in sorted order, two per thread: warps
+// become (almost) piece-uniform, alias rotations/columns are skipped warp-wide (23 of 40 slots are distinct on
+// average) and filled by copies.  Sorted positions are dealt out serpentine (t and 255 - t), so every warp gets a light
+// and a heavy half and the warps of a CTA finish together.  Results go into a [40][256] shared-memory tile at the env's
+// ORIGINAL position, so the tile leaves the SM as 40 contiguous 1 KB rows through the TMA bulk-copy engine
+// (cp.async.bulk, shared -> global): no per-thread store addressing at all.
+// =================================================================================================
+constexpr int ST = 128;                                   // threads per CTA
+constexpr int TILE = 2 * ST;                              // envs per tile
+constexpr int SORT_SMEM_BYTES = 40 * TILE * 4 + SCR_ROWS * ST * 4 + TAB_WORDS4 * 16 + TILE * 2 + 64;
+
+struct TileSink {                                          // packed words at the env's original column of the tile
+    uint32_t *out;                                         // s_out + original local id
+    __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * TILE] = word | (fl << 3); }
+    __device__ __forceinline__ void copy(int dst, int src, uint32_t extra) { out[dst * TILE] = out[src * TILE] | (extra << 3); }
+};
+
+__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+
+// sort key of an env from its chunks 2 and 3: pieces with the same rotation count adjacent (O | I S Z | L J T), no piece last
+__device__ __forceinline__ uint32_t sort_key(const uint4 &c, const uint4 &d) {
+    const uint32_t head = (d.w >> 8) & 0xFFu, np = (d.w >> 16) & 0xFFu;
+    if (head >= np) return 7u;
+    const uint32_t q[4] = {c.z, c.w, d.x, d.y};
+    return (0x0326541u >> (4 * queue_piece(q, head))) & 7u;                          // I L J T S Z O -> 1 4 5 6 2 3 0
+}
+
+__global__ void __launch_bounds__(ST, 4)
+afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words, int L, int M) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(smem_raw);                       // [40][TILE]
+    uint32_t *s_scr = s_out + 40 * TILE;                                            // [SCR_ROWS][ST]
+    uint4 *s_tab = reinterpret_cast<uint4 *>(s_scr + SCR_ROWS * ST);                // [TAB_WORDS4]
+    uint16_t *s_orig = reinterpret_cast<uint16_t *>(s_tab + TAB_WORDS4);            // [TILE] local id of each sorted position
+    int *s_cnt = reinterpret_cast<int *>(s_orig + TILE);                            // [8] counts, [8] bases
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int t = tid; t < TAB_WORDS4; t += ST) s_tab[t] = reinterpret_cast<const uint4 *>(c_orient)[t];
+    const int ntiles = (n + TILE - 1) / TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = (int64_t)tile * TILE;
+        const int cnt = min(TILE, (int)(n - base));
+        // ---- keys of this thread's two envs (local ids tid and tid + ST)
+        uint32_t key[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int lid = tid + h * ST;
+            key[h] = 7u;
+            if (lid < cnt) key[h] = sort_key(st[2 * stride + base + lid], st[3 * stride + base + lid]);
+        }
+        if (tid < 8) s_cnt[tid] = 0;
+        __syncthreads();
+        int wbase[2], rank[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, key[h]);
+            const int leader = __ffs(peers) - 1;
+            rank[h] = __popc(peers & ((1u << lane) - 1u));
+            int wb = 0;
+            if (lane == leader) wb = atomicAdd(&s_cnt[key[h]], __popc(peers));
+            wbase[h] = __shfl_sync(0xFFFFFFFFu, wb, leader);
+        }
+        __syncthreads();
+        if (tid < 32) {                                                             // exclusive prefix over the 8 keys
+            const int v = lane < 8 ? s_cnt[lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+            if (lane < 8) s_cnt[8 + lane] = incl - v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) s_orig[s_cnt[8 + key[h]] + wbase[h] + rank[h]] = (uint16_t)(tid + h * ST);
+        __syncthreads();
+        {   // pull the next tile's key chunks towards L2 while this tile is enumerated
+            const int64_t nb = base + (int64_t)gridDim.x * TILE + tid;
+            if (nb < n) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(st + 2 * stride + nb));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(st + 3 * stride + nb));
+            }
+            if (nb + ST < n) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(st + 2 * stride + nb + ST));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(st + 3 * stride + nb + ST));
+            }
+        }
+        // ---- enumerate sorted positions tid and TILE-1-tid (light + heavy half for every warp)
+        {   // both records of this thread: start them towards L1 now, so the second gather overlaps the first enumeration
+            const int l0 = s_orig[tid], l1 = s_orig[TILE - 1 - tid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (l0 < cnt) asm volatile("prefetch.global.L1 [%0];" :: "l"(st + j * stride + base + l0));
+                if (l1 < cnt) asm volatile("prefetch.global.L1 [%0];" :: "l"(st + j * stride + base + l1));
+            }
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int lid = s_orig[h == 0 ? tid : TILE - 1 - tid];
+            uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a, d = a;
+            if (lid < cnt) {
+                const int64_t i = base + lid;
+                a = st[i]; b = st[stride + i]; c = st[2 * stride + i]; d = st[3 * stride + i];
+            }
+            Env e; unpack_env(a, b, c, d, e);
+            TileSink sink{s_out + lid};
+            afterstates_env_impl<true>(e, s_tab, s_scr + tid, ST, L, M, sink);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to the bulk engine
+        __syncthreads();
+        if (tid < 40) {                                                             // 40 rows of TILE words per tile
+            for (int row = tid; row < 40; row += ST)
+                bulk_store_row(words + (size_t)row * (size_t)n + (size_t)base, s_out + row * TILE, (uint32_t)cnt * 4u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // smem may be reused once it has been read
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// fused hot-path step: move -> auto-reset of finished envs -> afterstates of the resulting state.
+// One launch reads each 64-byte record once and writes it once; the memory time of the move hides under the
+// integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
+// =================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(THREADS)
+step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
+                    int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
+                    const uint4 *__restrict__ pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
+                    uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M) {
+    __shared__ uint4 s_tab[TAB_WORDS4];
+    TPL_SCRATCH;
+    load_table(s_tab);
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+        Env e; load_env(st, stride, i, e);
+        const uint32_t was = e.state;
+        int k; bool changed;
+        const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
+        if (dlines) dlines[i] = (int8_t)k;
+        if (flags) flags[i] = (uint8_t)fl;
+        if (sto) sto[i] = (int8_t)e.state;
+        acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
+        if (was == S_RUNNING && e.state != S_RUNNING) {
+            acc[0] += 1;
+            if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+        }
+        if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {            // TPL_RESET_DONE semantics
+            uint32_t ep = episode ? episode[i] + 1u : 1u;
+            if (episode) episode[i] = ep;
+            install_config(e, pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
+            acc[7] += 1;
+            changed = true;
+        }
+        if (changed) {
+            st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+            st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+            st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+        }
+        st[3 * stride + i] = pack_meta(e);
+        GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n};
+        afterstates_env(e, s_tab, scr, THREADS, L, M, sink);
+    }
+    if (stats) flush_stats(acc, stats);
 }
 
 // =================================================================================================
@@ -208,6 +387,7 @@ rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool,
                uint32_t *tstep, unsigned long long *stats, int steps, uint64_t seed, uint64_t env_base,
                int gen_count, int L, int M, GreedyWeights gw) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    TPL_SCRATCH;
     load_table(s_tab);
     const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -216,8 +396,8 @@ rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool,
         Env e; load_env(st, stride, i, e);
         uint32_t ep = episode[i], t = tstep[i];
         for (int s = 0; s < steps; ++s) {
-            if (GREEDY) rollout_greedy_step(e, ep, t, acc, s_tab, pool, K, seed, env, gen_count, L, M, gw);
-            else rollout_random_step(e, ep, t, acc, s_tab, pool, K, seed, env, gen_count, L, M);
+            if (GREEDY) rollout_greedy_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
+            else rollout_random_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M);
         }
         store_env(st, stride, i, e);
         episode[i] = ep; tstep[i] = t;
@@ -236,12 +416,27 @@ static inline unsigned grid_for(int n) { return (unsigned)((n + THREADS - 1) / T
 
 // Grid-stride kernels: at most `blocks_per_sm` resident CTAs per SM, i.e. a multiple of the SM count (148 on
 // B200), so per-CTA set-up and the statistics flush are paid once per CTA slot instead of once per 128 envs.
-static unsigned grid_persistent(int n, int blocks_per_sm) {
+static int sm_count() {
     static int sms = 0;
     if (!sms) {
         int dev = 0; cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
+    return sms;
+}
+
+// The piece-sorted afterstate kernel (opt-in: TPL_SORTED_AFTERSTATES=1) moves its output tile with 16-byte-granular
+// bulk copies.  It executes 30 % fewer instructions than the plain kernel (58 M vs 82 M warp-instructions at 2^20 envs)
+// but exposes the record-gather latency and four CTA barriers per tile, and ends up at the same 0.12 ms
+// (profiles/r01_ncu_full_v3_afterstates_sorted.txt); it stays off until its loads are software-pipelined.
+static bool sorted_path_ok(int n, const void *feats) {
+    static int enabled = -1;
+    if (enabled < 0) { const char *v = getenv("TPL_SORTED_AFTERSTATES"); enabled = (v && v[0] == '1') ? 1 : 0; }
+    return enabled && n >= 2 * TILE && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
+}
+
+static unsigned grid_persistent(int n, int blocks_per_sm) {
+    const int sms = sm_count();
     if (blocks_per_sm <= 0) blocks_per_sm = 16;
     const unsigned need = grid_for(n), cap = (unsigned)(sms * blocks_per_sm);
     return need < cap ? need : cap;
@@ -310,11 +505,49 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
     const cudaStream_t s = (cudaStream_t)stream;
     const uint4 *st = (const uint4 *)state; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
     const unsigned g = grid_persistent(n, 8);
+    if (feats && !flags && !feats_f32 && sorted_path_ok(n, feats)) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(afterstates_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
+            if (e != cudaSuccess) return fail((int)e, "tpl_afterstates: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+        const int ntiles = (n + TILE - 1) / TILE;
+        const unsigned gs = (unsigned)(ntiles < 4 * sm_count() ? ntiles : 4 * sm_count());
+        afterstates_sorted_kernel<<<gs, ST, SORT_SMEM_BYTES, s>>>(st, plane_stride, n, w, L, M);
+        return check_launch("tpl_afterstates(sorted)");
+    }
     if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     return check_launch("tpl_afterstates");
+}
+
+int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
+                     int8_t *st, long long *stats, const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base,
+                     int gen_count, uint8_t *feats, uint8_t *aflags, float *feats_f32, int L, int M, void *stream) {
+    if (n < 0 || !state || !rot || !loc) return fail(TPL_EINVAL, "tpl_step_observe: null argument");
+    if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step_observe: plane_stride < n");
+    if (n > (1 << 25)) return fail(TPL_ERANGE, "tpl_step_observe: at most 2^25 envs per call (32-bit output offsets)");
+    if (pool && K <= 0) return fail(TPL_EINVAL, "tpl_step_observe: pool given but K <= 0");
+    if (gen_count < 0 || gen_count > TPL_MAX_PIECES) return fail(TPL_ERANGE, "tpl_step_observe: gen_count %d > 42", gen_count);
+    if (!feats && !feats_f32) return fail(TPL_EINVAL, "tpl_step_observe: no feature output requested");
+    if (feats_f32 && !aflags) return fail(TPL_EINVAL, "tpl_step_observe: the float form needs the flags array");
+    if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step_observe: L/M out of range");
+    if (n == 0) return 0;
+    const cudaStream_t s = (cudaStream_t)stream;
+    uint4 *sp = (uint4 *)state; const uint4 *pp = (const uint4 *)pool; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
+    unsigned long long *sq = (unsigned long long *)stats;
+    const unsigned g = grid_persistent(n, 8);
+#define TPL_SO(MODE) step_observe_kernel<MODE><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
+                                                                    seed, env_base, gen_count, w, aflags, f, L, M)
+    if (feats && !aflags) TPL_SO(0);
+    else if (feats && !feats_f32) TPL_SO(1);
+    else if (!feats) TPL_SO(2);
+    else TPL_SO(3);
+#undef TPL_SO
+    return check_launch("tpl_step_observe");
 }
 
 int tpl_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode, uint32_t episode0,

@@ -40,6 +40,8 @@ for i in range(tot):
         env.afterstates(packed=True); env.move(rot[i], loc[i]); env.reset(done_only=True)
     elif a.what == "afterstates_f32":
         env.afterstates(f32=True, u8=False); env.move(rot[i], loc[i]); env.reset(done_only=True)
+    elif a.what == "fused":
+        env.step_observe(rot[i], loc[i], packed=True)
     elif a.what == "rollout_random":
         env.rollout_random(32)
     elif a.what == "rollout_greedy":

@@ -23,7 +23,27 @@ struct HostSink {
     }
 };
 
+// sink with copy(): the packed staging the sorted kernel uses (word | flags << 3), one row of 40 per env
+struct PackedRowSink {
+    uint32_t row[40];
+    void put(int slot, uint32_t word, uint32_t fl) { row[slot] = word | (fl << 3); }
+    void copy(int dst, int src, uint32_t extra) { row[dst] = row[src] | (extra << 3); }
+};
+
 extern "C" {
+
+// afterstates through the warp-uniform (alias-skipping) variant, each env being its own one-lane "warp"
+int emul_afterstates_uniform(const void *state, int64_t stride, int n, uint8_t *feats_packed, int L, int M) {
+    uint32_t *out = (uint32_t *)feats_packed;
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env((const uint4 *)state, stride, i, e);
+        PackedRowSink sink; for (int s = 0; s < 40; ++s) sink.row[s] = 0xDEADBEEFu;
+        uint32_t scr[SCR_ROWS];
+        afterstates_env_impl<true>(e, table(), scr, 1, L, M, sink);
+        for (int s = 0; s < 40; ++s) out[(size_t)s * n + i] = sink.row[s];
+    }
+    return 0;
+}
 
 int emul_pack(void *out, int64_t stride, int aos, int n, const uint16_t *rows, const uint8_t *pieces, int pstride,
               const uint8_t *npieces, const int32_t *lines, const int32_t *moves, const int8_t *st, const uint8_t *head) {
@@ -83,7 +103,8 @@ int emul_step(void *state, int64_t stride, int n, const uint8_t *rot, const uint
     for (int64_t i = 0; i < n; ++i) {
         Env e; load_env(st, stride, i, e);
         int k; bool changed;
-        const uint32_t fl = step_env(e, table(), rot[i], loc[i], L, M, k, changed);
+        uint32_t scr[SCR_ROWS];
+        const uint32_t fl = step_env(e, table(), scr, 1, rot[i], loc[i], L, M, k, changed);
         if (changed) {
             st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
             st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
@@ -101,7 +122,42 @@ int emul_afterstates(const void *state, int64_t stride, int n, uint8_t *feats, u
     for (int64_t i = 0; i < n; ++i) {
         Env e; load_env((const uint4 *)state, stride, i, e);
         HostSink sink{(uint32_t *)feats, flags, ff, (size_t)n, (size_t)i};
-        afterstates_env(e, table(), L, M, sink);
+        uint32_t scr2[SCR_ROWS];
+        afterstates_env(e, table(), scr2, 1, L, M, sink);
+    }
+    return 0;
+}
+
+int emul_step_observe(void *state, int64_t stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
+                      int8_t *sto, long long *stats, const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base,
+                      int gen_count, uint8_t *feats, uint8_t *aflags, float *ff, int L, int M) {
+    uint4 *st = (uint4 *)state;
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env(st, stride, i, e);
+        const uint32_t was = e.state;
+        int k; bool changed;
+        uint32_t scr[SCR_ROWS];
+        const uint32_t fl = step_env(e, table(), scr, 1, rot[i], loc[i], L, M, k, changed);
+        if (dlines) dlines[i] = (int8_t)k;
+        if (flags) flags[i] = (uint8_t)fl;
+        if (sto) sto[i] = (int8_t)e.state;
+        if (stats) {
+            stats[6] += 1; stats[4] += k; stats[5] += changed ? 1 : 0;
+            if (was == S_RUNNING && e.state != S_RUNNING) {
+                stats[0] += 1;
+                if (fl & F_WIN) stats[1] += 1; else if (fl & F_TOPOUT) stats[2] += 1; else stats[3] += 1;
+            }
+        }
+        if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {
+            uint32_t ep = episode ? episode[i] + 1u : 1u;
+            if (episode) episode[i] = ep;
+            install_config(e, (const uint4 *)pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
+            if (stats) stats[7] += 1;
+        }
+        store_env(st, stride, i, e);
+        HostSink sink{(uint32_t *)feats, aflags, ff, (size_t)n, (size_t)i};
+        uint32_t scr2[SCR_ROWS];
+        afterstates_env(e, table(), scr2, 1, L, M, sink);
     }
     return 0;
 }
@@ -125,9 +181,10 @@ static int rollout(bool greedy, void *state, int64_t stride, int n, const void *
         const uint64_t env = env_base + (uint64_t)i;
         Env e; load_env(st, stride, i, e);
         uint32_t ep = episode[i], t = tstep[i];
+        uint32_t scr[SCR_ROWS];
         for (int s = 0; s < steps; ++s) {
-            if (greedy) rollout_greedy_step(e, ep, t, acc, table(), (const uint4 *)pool, K, seed, env, gen_count, L, M, gw);
-            else rollout_random_step(e, ep, t, acc, table(), (const uint4 *)pool, K, seed, env, gen_count, L, M);
+            if (greedy) rollout_greedy_step(e, ep, t, acc, table(), scr, 1, (const uint4 *)pool, K, seed, env, gen_count, L, M, gw);
+            else rollout_random_step(e, ep, t, acc, table(), scr, 1, (const uint4 *)pool, K, seed, env, gen_count, L, M);
         }
         store_env(st, stride, i, e);
         episode[i] = ep; tstep[i] = t;

@@ -44,7 +44,9 @@ class EmulEngine:
             "reset_from_pool": [P, I64, I, P, I, P, P, I, P, U64, U64, I],
             "step": [P, I64, I, P, P, P, P, P, I, I],
             "afterstates": [P, I64, I, P, P, P, I, I],
+            "afterstates_uniform": [P, I64, I, P, I, I],
             "gen_pieces": [P, I, I, U64, U64, P, U32],
+            "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, U64, U64, I, P, P, P, I, I],
             "rollout_random": [P, I64, I, P, I, P, P, P, I, U64, U64, I, I, I],
             "rollout_greedy": [P, I64, I, P, I, P, P, P, I, P, U64, U64, I, I, I],
         }
@@ -111,12 +113,27 @@ class EmulEngine:
     def afterstates_packed(self, s, L, M):
         feats = np.zeros((40, s.n, 4), np.uint8)
         self.L.emul_afterstates(_np_ptr(s.planes), s.stride, s.n, _np_ptr(feats), None, None, L, M)
+        uni = np.zeros((40, s.n, 4), np.uint8)          # the alias-skipping variant must give the same bytes
+        self.L.emul_afterstates_uniform(_np_ptr(s.planes), s.stride, s.n, _np_ptr(uni), L, M)
+        assert np.array_equal(uni, feats), "warp-uniform afterstate variant differs from the plain one"
         return feats.reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
 
     def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
         idx = self._c(idx, np.int32); mask = self._c(mask, np.uint8)
         self.L.emul_reset_from_pool(_np_ptr(s.planes), s.stride, s.n, _np_ptr(pool), pool.shape[0], _np_ptr(idx), _np_ptr(mask),
                                     mode, _np_ptr(episode), seed, env_base, gen_count)
+
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False):
+        n = s.n
+        rot = np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8)
+        loc = np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8)
+        dl, fl, st = np.zeros(n, np.int8), np.zeros(n, np.uint8), np.zeros(n, np.int8)
+        feats, afl = np.zeros((40, n, 4), np.uint8), (None if packed else np.zeros((40, n), np.uint8))
+        stats = np.zeros(8, np.int64)
+        self.L.emul_step_observe(_np_ptr(s.planes), s.stride, n, _np_ptr(rot), _np_ptr(loc), _np_ptr(dl), _np_ptr(fl), _np_ptr(st),
+                                 _np_ptr(stats), _np_ptr(pool), pool.shape[0], _np_ptr(episode), seed, env_base, 0,
+                                 _np_ptr(feats), _np_ptr(afl), None, L, M)
+        return dl, fl, st, feats, afl, stats
 
     def gen_pieces(self, n, count, seed, env_base, episode0=0, episode=None):
         out = np.zeros((n, count), np.uint8)
@@ -245,6 +262,22 @@ class GpuEngine:
                   "tpl_reset_from_pool")
         if episode is not None:
             episode[:] = d_ep.cpu().numpy().view(np.uint32)
+
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False):
+        t = self.torch; n = s.n
+        rot = self._t(np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8), np.uint8)
+        loc = self._t(np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8), np.uint8)
+        z = lambda shape, dt: t.zeros(shape, dtype=dt, device=self.dev)     # noqa: E731
+        dl, fl, st = z(n, t.int8), z(n, t.uint8), z(n, t.int8)
+        feats, afl = z((40, n, 4), t.uint8), (None if packed else z((40, n), t.uint8))
+        stats = z(8, t.int64)
+        d_ep = self._t(episode, np.uint32)
+        self._chk(self.L.tpl_step_observe(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
+                                          self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), seed, env_base, 0,
+                                          self._p(feats), self._p(afl), None, L, M, self._stream()), "tpl_step_observe")
+        episode[:] = d_ep.cpu().numpy().view(np.uint32)
+        return (dl.cpu().numpy(), fl.cpu().numpy(), st.cpu().numpy(), feats.cpu().numpy(),
+                None if afl is None else afl.cpu().numpy(), stats.cpu().numpy())
 
     def gen_pieces(self, n, count, seed, env_base, episode0=0, episode=None):
         t = self.torch

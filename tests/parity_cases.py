@@ -300,6 +300,45 @@ def case_rollout(eng, pool_arrays, n, steps, L, M, seed, env_base, weights=None,
     return stats
 
 
+def case_fused_step_observe(eng, pool_arrays, n=3000, steps=45, L=10, M=30, seed=8, env_base=123456789):
+    """The fused kernel (move -> auto-reset -> afterstates) == the three separate calls, and == the oracle."""
+    prow, ppieces, pnp = pool_arrays
+    pool = eng.make_pool(prow, ppieces, pnp)
+    rng = np.random.default_rng(seed)
+    a, b = eng.empty_states(n), eng.empty_states(n)
+    ep_a, ep_b = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    eng.reset(a, pool, episode=ep_a, seed=seed, env_base=env_base)
+    eng.reset(b, pool, episode=ep_b, seed=seed, env_base=env_base)
+    ost = c_oracle.BatchState(n)
+    oep, ots, _ = c_oracle.rollout(ost, env_base, seed, L, M, prow, ppieces, pnp, 0, True)
+    tot = np.zeros(8, np.int64)
+    for t in range(steps):
+        rot, loc = rng.integers(0, 4, n), rng.integers(0, 10, n)
+        dl, fl, st, feats, afl, stats = eng.step_observe(a, rot, loc, pool, ep_a, seed, env_base, L, M, packed=(t % 2 == 1))
+        tot += stats
+        dl2, fl2, st2 = eng.step(b, rot, loc, L, M)
+        eng.reset(b, pool, mode=2, episode=ep_b, seed=seed, env_base=env_base)
+        f2, g2 = eng.afterstates(b, L, M)
+        f2 = f2.reshape(n, 40, 4).transpose(1, 0, 2).copy(); g2 = g2.reshape(n, 40).T
+        assert np.array_equal(dl, dl2) and np.array_equal(fl, fl2) and np.array_equal(st, st2)
+        assert np.array_equal(ep_a, ep_b) and np.array_equal(eng.raw(a), eng.raw(b))
+        if afl is None:
+            f2[:, :, 0] |= (g2 << 3)
+        else:
+            assert np.array_equal(afl, g2)
+        assert np.array_equal(feats, f2)
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        assert np.array_equal(dl, odl) and np.array_equal(st, ost.state)
+        done = np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]
+        for i in done:
+            oep[i] += 1
+            k = po.config_index(seed, env_base + int(i), int(oep[i]), len(prow))
+            ost.rows[i] = prow[k]; ost.pieces[i] = ppieces[k]; ost.npieces[i] = pnp[k]
+            ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
+        assert_same(eng, a, ost, f"fused step {t}")
+    assert tot[6] == n * steps and tot[0] > 0 and tot[7] == tot[0]
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases the reference's semantics single out (SURVEY.md section 8c micro-cases)
 # ---------------------------------------------------------------------------------------------

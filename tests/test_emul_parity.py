@@ -55,5 +55,9 @@ def test_rollout_greedy(emul, golden_dir):
     assert stats[1] > 0          # a sensible greedy policy wins some carve configs
 
 
+def test_fused_step_observe(emul, golden_dir):
+    pc.case_fused_step_observe(emul, _pool(golden_dir))
+
+
 def test_edges(emul):
     pc.case_edges(emul)

@@ -65,5 +65,26 @@ def test_rollout_greedy(gpu, golden_dir):
     assert stats[1] > 0
 
 
+def test_fused_step_observe(gpu, golden_dir):
+    pc.case_fused_step_observe(gpu, _pool(golden_dir))
+
+
 def test_edges(gpu):
     pc.case_edges(gpu)
+
+
+def test_sorted_afterstates_kernel_opt_in(gpu):
+    """The opt-in piece-sorted kernel (TPL_SORTED_AFTERSTATES=1; counting sort in shared memory, warp-uniform alias
+    skipping, TMA bulk stores) must produce the same bytes.  The switch is read once per process: run it in a child."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests.engines import GpuEngine\n"
+            "from tests import parity_cases as pc\n"
+            "g = GpuEngine()\n"
+            "pc.case_afterstates_vs_oracle(g, 100_000, 10, 30, 5)\n"
+            "pc.case_afterstates_vs_oracle(g, 4100, 15, 40, 9)\n"
+            "print('sorted-ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TPL_SORTED_AFTERSTATES="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sorted-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
