@@ -343,7 +343,7 @@ def extra_single_gpu(tp, torch, dev, pool, args):
         e0.record(s); g.replay(); e1.record(s); s.synchronize()
     ms = e0.elapsed_time(e1)
     out["config_4096_envs"] = {"afterstates_per_s": 4096 * 40 * iters / (ms * 1e-3), "us_per_call": ms * 1e3 / iters,
-                               "note": "BASELINE configs[1]; 28 CTAs < 148 SMs, latency-bound; 1000 calls in one CUDA graph; inputs L2-resident"}
+                               "note": "BASELINE configs[1]; sub-wave problem (latency-bound): one thread per (env, rotation), 128 CTAs; 1000 calls in one CUDA graph; inputs L2-resident"}
     # fused rollouts (state in registers across steps)
     n = args.envs_per_gpu
     env = tp.BatchedTetris(n, L_LINES, M_MOVES, device=dev, seed=SEED, config_pool=pool)

@@ -140,11 +140,14 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
 // the warp must call it (no early exit), rotations that are aliases for every lane (r >= max n_rot in the warp) and
 // columns no lane can reach (c > max(10 - w)) are not enumerated but copied from the slot they alias -- on average
 // 23 of the 40 slots are distinct placements.  Needs a sink with copy(dst, src, extra_flags).
+// [r_begin, r_end) restricts the enumeration to some rotations (the small-batch kernel gives each rotation of an env
+// to its own thread); deferred line-clear slots still write every alias row of the rotation that owns them.
 template <bool UNIFORM, class Sink>
-__device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink) {
+__device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
+                                                     int r_begin = 0, int r_end = 4) {
     const bool nopiece = e.head >= e.npieces;
     if (!UNIFORM && nopiece) {
-        for (int s = 0; s < 40; ++s) sink.put(s, 0u, F_NOPIECE);
+        for (int s = r_begin * 10; s < r_end * 10; ++s) sink.put(s, 0u, F_NOPIECE);
         return;
     }
     // a lane without a piece walks through as an O piece (its stores are overwritten at the end)
@@ -191,7 +194,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
     unsigned long long pending = 0ull;
 
-    for (int r = 0; r < nrot_warp; ++r) {
+    for (int r = r_begin; r < (UNIFORM ? nrot_warp : r_end); ++r) {
         const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
         const int w = orient_w(o);
         int cmax_warp = 9;
@@ -240,8 +243,9 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
 }
 
 template <class Sink>
-__device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink) {
-    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink);
+__device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
+                                                int r_begin = 0, int r_end = 4) {
+    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink, r_begin, r_end);
 }
 
 // ---------------------------------------------------------------------------------------------

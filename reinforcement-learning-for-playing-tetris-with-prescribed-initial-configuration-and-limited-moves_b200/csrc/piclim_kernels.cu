@@ -191,6 +191,25 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
     }
 }
 
+// Small batches (BASELINE configs[1]: 4096 envs = 32 CTAs on 148 SMs) are latency-bound: one warp per scheduler runs a
+// 2 000-instruction dependent stream.  This variant gives each (env, rotation) pair its own thread: 4x the threads, a
+// 4x shorter critical path, at the price of repeating the per-env set-up in the four threads of an env.
+template <int MODE>
+__global__ void __launch_bounds__(THREADS)
+afterstates_split_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
+                         uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
+    __shared__ uint4 s_tab[TAB_WORDS4];
+    TPL_SCRATCH;
+    load_table(s_tab);
+    const int64_t idx = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    const int64_t i = idx >> 2;
+    const int r = (int)(idx & 3);
+    if (i >= n) return;
+    Env e; load_env(st, stride, i, e);
+    GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n};
+    afterstates_env(e, s_tab, scr, THREADS, L, M, sink, r, r + 1);
+}
+
 // =================================================================================================
 // afterstates, piece-sorted tiles (compact output form).
 //
@@ -516,6 +535,14 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
         const unsigned gs = (unsigned)(ntiles < 4 * sm_count() ? ntiles : 4 * sm_count());
         afterstates_sorted_kernel<<<gs, ST, SORT_SMEM_BYTES, s>>>(st, plane_stride, n, w, L, M);
         return check_launch("tpl_afterstates(sorted)");
+    }
+    if (grid_for(n) < 2u * (unsigned)sm_count()) {                 // fewer than two CTAs per SM: split envs over 4 threads
+        const unsigned g4 = (unsigned)(((int64_t)n * 4 + THREADS - 1) / THREADS);
+        if (feats && !flags) afterstates_split_kernel<0><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+        else if (feats && !feats_f32) afterstates_split_kernel<1><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+        else if (!feats) afterstates_split_kernel<2><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+        else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+        return check_launch("tpl_afterstates(split)");
     }
     if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);

@@ -45,6 +45,18 @@ int emul_afterstates_uniform(const void *state, int64_t stride, int n, uint8_t *
     return 0;
 }
 
+// afterstates with each rotation enumerated by a separate call (the small-batch kernel's thread mapping)
+int emul_afterstates_split(const void *state, int64_t stride, int n, uint8_t *feats_packed, int L, int M) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int r = 3; r >= 0; --r) {                     // any order must work
+            Env e; load_env((const uint4 *)state, stride, i, e);
+            HostSink sink{(uint32_t *)feats_packed, nullptr, nullptr, (size_t)n, (size_t)i};
+            uint32_t scr[SCR_ROWS];
+            afterstates_env(e, table(), scr, 1, L, M, sink, r, r + 1);
+        }
+    return 0;
+}
+
 int emul_pack(void *out, int64_t stride, int aos, int n, const uint16_t *rows, const uint8_t *pieces, int pstride,
               const uint8_t *npieces, const int32_t *lines, const int32_t *moves, const int8_t *st, const uint8_t *head) {
     for (int64_t i = 0; i < n; ++i) {

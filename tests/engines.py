@@ -45,6 +45,7 @@ class EmulEngine:
             "step": [P, I64, I, P, P, P, P, P, I, I],
             "afterstates": [P, I64, I, P, P, P, I, I],
             "afterstates_uniform": [P, I64, I, P, I, I],
+            "afterstates_split": [P, I64, I, P, I, I],
             "gen_pieces": [P, I, I, U64, U64, P, U32],
             "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, U64, U64, I, P, P, P, I, I],
             "rollout_random": [P, I64, I, P, I, P, P, P, I, U64, U64, I, I, I],
@@ -116,6 +117,9 @@ class EmulEngine:
         uni = np.zeros((40, s.n, 4), np.uint8)          # the alias-skipping variant must give the same bytes
         self.L.emul_afterstates_uniform(_np_ptr(s.planes), s.stride, s.n, _np_ptr(uni), L, M)
         assert np.array_equal(uni, feats), "warp-uniform afterstate variant differs from the plain one"
+        spl = np.full((40, s.n, 4), 0xEE, np.uint8)     # and so must the one-thread-per-rotation variant
+        self.L.emul_afterstates_split(_np_ptr(s.planes), s.stride, s.n, _np_ptr(spl), L, M)
+        assert np.array_equal(spl, feats), "rotation-split afterstate variant differs from the plain one"
         return feats.reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
 
     def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
