@@ -7,7 +7,7 @@ calls:   Tetris.move with the chosen action  ->  auto-reset of finished episodes
 (tpl_step_observe); the three stand-alone kernels it fuses (tpl_step, tpl_reset_from_pool, tpl_afterstates) are timed
 separately after the timed region and reported under "kernels".
 Workload at N GPUs: 2^20 envs per GPU (BASELINE.json configs[2] at N=1, configs[4] = 8M envs at N=8), L=10, M=30,
-pool = 4096 synthetic prescribed boards + the 256 carve-generated configs of tests/golden; weak scaling, envs sharded
+pool = 4096 synthetic prescribed boards + 4096 carve-generated configs; weak scaling, envs sharded
 by global env id, one NCCL all-reduce of the 64-byte episode-stats vector per rollout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs-per-gpu E]
@@ -51,7 +51,9 @@ def load_peaks():
 
 
 def make_pool(tp):
-    carve = tp.load_pool(os.path.join(ROOT, "tests", "golden", "carve_pool_L10_M30.npz"))
+    """4096 carve-generated prescribed configs (native generator, bit-identical to the reference's
+    random.seed(k); Tetris(10, 30, warm_reset=False) for k = 0..4095) + 4096 synthetic boards."""
+    carve = tp.carve_pool(4096, L_LINES, M_MOVES, seed0=0, with_solutions=False)
     return tp.concat_pools(tp.synthetic_pool(4096, seed=SEED, M=M_MOVES), carve)
 
 
@@ -183,8 +185,8 @@ def run_reference(args):
 
 def workload_config(args, n_total):
     return {"workload": "2^20 envs/GPU x [40-slot afterstate enumeration + features -> move -> auto-reset], "
-                        "prescribed-config pool (4096 synthetic + 256 carve), L=10 M=30 (BASELINE configs[2]; configs[4] at 8 GPUs)",
-            "envs_per_gpu": args.envs_per_gpu, "envs_total": n_total, "L": L_LINES, "M": M_MOVES, "pool": 4352,
+                        "prescribed-config pool (4096 synthetic + 4096 carve-generated), L=10 M=30 (BASELINE configs[2]; configs[4] at 8 GPUs)",
+            "envs_per_gpu": args.envs_per_gpu, "envs_total": n_total, "L": L_LINES, "M": M_MOVES, "pool": 8192,
             "l2": "working set per step (64 MiB state r+w, 160 MiB afterstate outputs) exceeds the 126 MB L2",
             "parallelism": f"envs sharded by global env id over {args.gpus} GPU(s); one 64-byte NCCL all-reduce per rollout"}
 

@@ -52,5 +52,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+CARVE_LIB_PATH = os.path.join(CSRC, "libpiclim_carve.so")
+
+
+def build_carve(force: bool = False) -> str:
+    """The native prescribed-config generator (host code, g++)."""
+    src = os.path.join(CSRC, "carve_gen.cpp")
+    if force or not os.path.exists(CARVE_LIB_PATH) or os.path.getmtime(CARVE_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", CARVE_LIB_PATH, src])
+    return CARVE_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

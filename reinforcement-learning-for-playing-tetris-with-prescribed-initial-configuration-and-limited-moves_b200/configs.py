@@ -123,6 +123,31 @@ def synthetic_pool(K: int, seed: int = 0, M: int = 30, max_height: int = 12, fil
     return ConfigPool(rows, pieces, np.full(K, M + 1, np.uint8))
 
 
+def carve_pool(K: int, L: int, M: int, seed0: int = 0, threads: Optional[int] = None, with_solutions: bool = True) -> ConfigPool:
+    """K prescribed configs from the native carving generator (csrc/carve_gen.cpp): config k is exactly what the
+    reference produces for random.seed(seed0 + k); Tetris(L, M, warm_reset=False, debug=True)
+    (game/tetris.py:226-352) -- board, the M+1 pieces and the recorded solution -- at native speed, threaded."""
+    import ctypes
+    import os
+    from . import build as _build
+    if M + 1 > MAX_PIECES:
+        raise ValueError("M + 1 pieces must fit the 42-piece queue")
+    lib = ctypes.CDLL(_build.build_carve())
+    lib.carve_generate.restype = ctypes.c_int
+    lib.carve_generate.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2 +         [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int]
+    rows = np.zeros((K, 20), np.uint16)
+    pieces = np.zeros((K, MAX_PIECES), np.uint8)
+    npieces = np.zeros(K, np.uint8)
+    sols = np.full((K, M, 2), -1, np.int8) if with_solutions else None
+    nsol = np.zeros(K, np.uint8)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None       # noqa: E731
+    rc = lib.carve_generate(int(seed0), K, L, M, p(rows), p(pieces), MAX_PIECES, p(npieces), p(sols), p(nsol),
+                            int(threads or os.cpu_count() or 1))
+    if rc != 0:
+        raise ValueError("carve_generate rejected its arguments (1 <= L <= 16, M >= 1)")
+    return ConfigPool(rows, pieces, npieces, sols, nsol)
+
+
 def load_pool(path: str) -> ConfigPool:
     z = np.load(path)
     pieces = np.zeros((z["rows"].shape[0], MAX_PIECES), np.uint8)
