@@ -40,7 +40,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB_PATH
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("TPL_NVCC_EXTRA", "").split()          # tuning experiments only (e.g. -DTPL_AS_MINBLOCKS=3)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as f:

@@ -97,15 +97,16 @@ __device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, ui
 }
 
 template <int C, class Sink>
-__device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS], const uint32_t (&col)[14],
+__device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS], const uint32_t (&H16)[12],
+                                          const uint32_t (&col)[14],
                                           const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
                                           uint32_t flN, uint32_t flT, bool canon, int w,
                                           int bo0, int bo1, int bo2, int bo3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO01, uint32_t TO23, uint32_t hm, int thr,
                                           uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, int cmax_warp) {
     if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
-        fl |= F_ALIAS;
-        if (!pend) sink.put(r * 10 + C, word, fl);
+        if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
+        else { fl |= F_ALIAS; if (!pend) sink.put(r * 10 + C, word, fl); }
         return;
     }
     const int y = max(max(H[C] - bo0, H[C + 1] - bo1), max(H[C + 2] - bo2, H[C + 3] - bo3));
@@ -114,26 +115,63 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & (col[C] | mul_fma_pipe(cb0, pw)) & (col[C + 1] | mul_fma_pipe(cb1, pw)) &
                           (col[C + 2] | mul_fma_pipe(cb2, pw)) & (col[C + 3] | mul_fma_pipe(cb3, pw));
     const uint32_t Y2 = (uint32_t)y * 0x10001u;
-    const uint32_t N01 = __viaddmax_s16x2(Y2, TO01, __byte_perm(Hw[C], 0u, 0x4140));
-    const uint32_t N23 = __viaddmax_s16x2(Y2, TO23, __byte_perm(Hw[C], 0u, 0x4342));
+    const uint32_t N01 = __viaddmax_s16x2(Y2, TO01, H16[C]);          // H16[c] = (H[c], H[c+1]) as s16x2
+    const uint32_t N23 = __viaddmax_s16x2(Y2, TO23, H16[C + 2]);
     const uint32_t N4 = __byte_perm(N01, N23, 0x6420);
     const uint32_t agg2 = __vsadu4(N4, Hw[C]) + agg;
     const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
     uint32_t wnew = agg2 * 0x01000100u + K;
     wnew = b2 * 0x10000u + wnew;
-    wnew = top ? U : wnew;
-    const uint32_t fnew = top ? flT : flN;
     const bool pnew = !top && full != 0u;
-    if (C <= 6) {                                  // every width fits (w <= 4)
-        word = wnew; fl = fnew; pend = pnew;
-    } else {                                       // loc clamps to 10 - w (:364): repeat the last fitting column
-        const bool fits = C + w <= COLS;
-        word = fits ? wnew : word;
-        fl = fits ? fnew : (fl | F_ALIAS);
-        pend = fits ? pnew : pend;
+    if constexpr (Sink::PACKED) {
+        // compact form: the flags ride in byte 0 (K and U already carry flN << 3 / flT << 3 for this rotation)
+        wnew = top ? U : wnew;
+        if (C <= 6) { word = wnew; pend = pnew; }
+        else {
+            const bool fits = C + w <= COLS;
+            word = fits ? wnew : (word | (F_ALIAS << 3));
+            pend = fits ? pnew : pend;
+        }
+        if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
+        if (!pend) sink.put_packed_col(C, word);
+    } else {
+        wnew = top ? U : wnew;
+        const uint32_t fnew = top ? flT : flN;
+        if (C <= 6) {                                  // every width fits (w <= 4)
+            word = wnew; fl = fnew; pend = pnew;
+        } else {                                       // loc clamps to 10 - w (:364): repeat the last fitting column
+            const bool fits = C + w <= COLS;
+            word = fits ? wnew : word;
+            fl = fits ? fnew : (fl | F_ALIAS);
+            pend = fits ? pnew : pend;
+        }
+        if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
+        if (!pend) sink.put(r * 10 + C, word, fl);
     }
-    if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
-    if (!pend) sink.put(r * 10 + C, word, fl);
+}
+
+// What a deferred (row-completing) slot needs besides the ten columns
+struct PendingCtx { unsigned long long mask; uint32_t piece, cells, lines, fl_noclear; };
+
+// One deferred slot: the general move on a copy of the columns, features of the cleared board, and the stores to the
+// slot and to every slot that aliases it (rot + k * n_rot, and loc > 10 - w when the slot is the last fitting column).
+template <class Sink>
+__device__ __forceinline__ void resolve_slot(const uint32_t (&cols)[COLS], const PendingCtx &cx, int s, const uint4 *tab,
+                                             uint32_t *scr, int ss, int L, Sink &sink) {
+    const int r = s / 10, c = s - 10 * r;
+    const uint4 o = tab[(cx.piece * 4 + r) * 2], ob = tab[(cx.piece * 4 + r) * 2 + 1];
+    uint32_t x[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) x[k] = cols[k];
+    const MoveOut m = place_general(x, scr, ss, o, ob, c);
+    const uint32_t f3 = board_features(x, (int)cx.cells + 4 - 10 * m.k);
+    const uint32_t word = (uint32_t)m.k | (f3 << 8);
+    const uint32_t fl = m.k == 0 ? cx.fl_noclear : (((int)cx.lines + m.k >= L) ? F_WIN : cx.fl_noclear);   // :389-391, :415-422
+    const int nrot = orient_nrot(o), w = orient_w(o);
+    const int cend = (c == COLS - w) ? COLS - 1 : c;
+    for (int r2 = r; r2 < 4; r2 += nrot)
+        for (int c2 = c; c2 <= cend; ++c2)
+            sink.put(r2 * 10 + c2, word, fl | ((r2 != r || c2 != c) ? F_ALIAS : 0u));
 }
 
 // UNIFORM = true is the variant for warps whose lanes were sorted by piece (afterstates_sorted_kernel): every lane of
@@ -142,9 +180,12 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
 // 23 of the 40 slots are distinct placements.  Needs a sink with copy(dst, src, extra_flags).
 // [r_begin, r_end) restricts the enumeration to some rotations (the small-batch kernel gives each rotation of an env
 // to its own thread); deferred line-clear slots still write every alias row of the rotation that owns them.
+// `defer` != nullptr: the deferred slots are not resolved here but returned (mask + context), so that a CTA can pool
+// them and resolve them with full warps (see afterstates_kernel).
 template <bool UNIFORM, class Sink>
 __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
-                                                     int r_begin = 0, int r_end = 4) {
+                                                     int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr) {
+    if (defer) defer->mask = 0ull;
     const bool nopiece = e.head >= e.npieces;
     if (!UNIFORM && nopiece) {
         for (int s = r_begin * 10; s < r_end * 10; ++s) sink.put(s, 0u, F_NOPIECE);
@@ -171,6 +212,9 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     Hw[1] = __byte_perm(HB0, HB1, 0x4321); Hw[2] = __byte_perm(HB0, HB1, 0x5432); Hw[3] = __byte_perm(HB0, HB1, 0x6543);
     Hw[5] = __byte_perm(HB1, HB2, 0x4321); Hw[6] = __byte_perm(HB1, HB2, 0x5432); Hw[7] = __byte_perm(HB1, HB2, 0x6543);
     Hw[9] = HB2 >> 8;
+    uint32_t H16[12];                                // H16[c] = (H[c], H[c+1]) as s16x2, zero beyond column 9
+#pragma unroll
+    for (int c = 0; c < 12; ++c) H16[c] = (uint32_t)H[c] | ((uint32_t)H[c + 1] << 16);
     const uint32_t agg = __vsadu4(HB0, 0u) + __vsadu4(HB1, 0u) + __vsadu4(HB2, 0u);
     const uint32_t bump = __vsadu4(Hw[0], Hw[1]) + __vsadu4(Hw[4], Hw[5]) + (uint32_t)__sad(H[8], H[9], 0u);
     uint32_t Bb[COLS];                               // bump minus the pairs a placement at c can change
@@ -204,32 +248,23 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const uint32_t afl = orient_alias(o) ? F_ALIAS : 0u;
         const bool canon = afl == 0u;
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
+        const uint32_t Kr = Sink::PACKED ? K + (flN << 3) : K, Ur = Sink::PACKED ? (U | (flT << 3)) : U;
         uint32_t word = 0, fl = 0, pmask = 0; bool pend = false;
-#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, K, U, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
+        if constexpr (Sink::PACKED) sink.begin_rotation(r);
+#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, H16, col, A, Bb, agg, Kr, Ur, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
                                  o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         pending |= (unsigned long long)pmask << (10 * r);
     }
 
-    // ---- deferred line-clear slots: the general move on a copy of the columns
+    // ---- deferred line-clear slots
+    PendingCtx cx{pending, piece, cells, e.lines, fl_noclear};
+    if (defer) { *defer = cx; return; }
     while (pending) {
         const int s = __ffsll((long long)pending) - 1;
         pending &= pending - 1ull;
-        const int r = s / 10, c = s - 10 * r;
-        const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
-        uint32_t x[COLS];
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) x[k] = e.col[k];
-        const MoveOut m = place_general(x, scr, ss, o, ob, c);
-        const uint32_t f3 = board_features(x, (int)cells + 4 - 10 * m.k);
-        const uint32_t word = (uint32_t)m.k | (f3 << 8);
-        const uint32_t fl = m.k == 0 ? fl_noclear : (((int)e.lines + m.k >= L) ? F_WIN : fl_noclear);   // :389-391, :415-422
-        const int nrot = orient_nrot(o), w = orient_w(o);
-        const int cend = (c == COLS - w) ? COLS - 1 : c;
-        for (int r2 = r; r2 < 4; r2 += nrot)
-            for (int c2 = c; c2 <= cend; ++c2)
-                sink.put(r2 * 10 + c2, word, fl | ((r2 != r || c2 != c) ? F_ALIAS : 0u));
+        resolve_slot(e.col, cx, s, tab, scr, ss, L, sink);
     }
 
     if constexpr (UNIFORM) {
@@ -244,8 +279,8 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
 
 template <class Sink>
 __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
-                                                int r_begin = 0, int r_end = 4) {
-    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink, r_begin, r_end);
+                                                int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr) {
+    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink, r_begin, r_end, defer);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,6 +312,7 @@ __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32
 //           + (lose or top-out ? w[5] : 0)
 // ---------------------------------------------------------------------------------------------
 struct GreedySink {
+    static constexpr bool PACKED = false;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {

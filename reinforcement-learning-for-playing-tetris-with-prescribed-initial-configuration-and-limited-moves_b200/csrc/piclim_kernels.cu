@@ -164,8 +164,13 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
 // 32-bit offset serves every array and a warp's store of one slot is one contiguous 128-byte line.
 template <int MODE>
 struct GlobalSink {
+    static constexpr bool PACKED = (MODE == 0);
     uint32_t *words; uint8_t *flags; float4 *ff;      // already offset by the env index
     uint32_t n;
+    uint32_t *wrot;                                   // row of the current rotation's column 0
+    __device__ __forceinline__ void begin_rotation(int r) { wrot = words + (size_t)((uint32_t)(r * 10) * n); }
+    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { wrot[(uint32_t)c * n] = packed; }
+    __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { words[(uint32_t)slot * n] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
         const uint32_t o = (uint32_t)slot * n;
         if (MODE == 0) words[o] = word | (fl << 3);
@@ -177,17 +182,76 @@ struct GlobalSink {
     }
 };
 
+// ---- CTA-pooled resolution of the deferred (row-completing) slots -----------------------------------------------
+// Only ~2 lanes of a warp have such a slot in any given iteration, so resolving them in place runs the ~240-instruction
+// general move at 7 % lane utilisation (20 % of the kernel's issue slots on carve-generated boards).  Instead every
+// thread appends its deferred slots to a shared list, parks its ten columns in shared memory, and after one barrier
+// the list is worked off by consecutive threads: full warps, and most warps skip the phase altogether.
+struct CoopSmem {
+    uint32_t env[12 * THREADS];       // [k][tid]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines
+    uint16_t items[40 * THREADS];     // owner tid | slot << 8
+    int n_items;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void coop_publish(CoopSmem &cs, const Env &e, const PendingCtx &cx) {
+    if (!cx.mask) return;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) cs.env[k * THREADS + tid] = e.col[k];
+    cs.env[10 * THREADS + tid] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
+    cs.env[11 * THREADS + tid] = cx.lines;
+    unsigned long long m = cx.mask;
+    int at = atomicAdd(&cs.n_items, __popcll(m));
+    while (m) {
+        const int s = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        cs.items[at++] = (uint16_t)(tid | (s << 8));
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void coop_resolve(CoopSmem &cs, const uint4 *s_tab, uint32_t *scr, int64_t tile_base, uint32_t n,
+                                             uint32_t *words, uint8_t *flags, float4 *ff, int L) {
+    const int total = cs.n_items;
+    for (int k = threadIdx.x; k < total; k += THREADS) {
+        const int item = cs.items[k], owner = item & 0xFF, slot = item >> 8;
+        uint32_t cols[COLS];
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) cols[j] = cs.env[j * THREADS + owner];
+        const uint32_t m0 = cs.env[10 * THREADS + owner];
+        const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, cs.env[11 * THREADS + owner], m0 >> 16};
+        const int64_t i = tile_base + owner;
+        GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, nullptr};
+        resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
+    }
+}
+
+#ifndef TPL_AS_MINBLOCKS
+#define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    __shared__ CoopSmem cs;
     TPL_SCRATCH;
     load_table(s_tab);
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        Env e; load_env(st, stride, i, e);
-        GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n};
-        afterstates_env(e, s_tab, scr, THREADS, L, M, sink);
+    const int ntiles = (n + THREADS - 1) / THREADS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
+        const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
+        if (threadIdx.x == 0) cs.n_items = 0;
+        __syncthreads();
+        if (i < n) {
+            Env e; load_env(st, stride, i, e);
+            GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
+            PendingCtx cx;
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            coop_publish<MODE>(cs, e, cx);
+        }
+        __syncthreads();
+        coop_resolve<MODE>(cs, s_tab, scr, base, (uint32_t)n, words, flags, ff, L);
     }
 }
 
@@ -206,7 +270,7 @@ afterstates_split_kernel(const uint4 *__restrict__ st, int64_t stride, int n, ui
     const int r = (int)(idx & 3);
     if (i >= n) return;
     Env e; load_env(st, stride, i, e);
-    GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n};
+    GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
     afterstates_env(e, s_tab, scr, THREADS, L, M, sink, r, r + 1);
 }
 
@@ -228,7 +292,12 @@ constexpr int TILE = 2 * ST;                              // envs per tile
 constexpr int SORT_SMEM_BYTES = 40 * TILE * 4 + SCR_ROWS * ST * 4 + TAB_WORDS4 * 16 + TILE * 2 + 64;
 
 struct TileSink {                                          // packed words at the env's original column of the tile
+    static constexpr bool PACKED = true;
     uint32_t *out;                                         // s_out + original local id
+    uint32_t *orot;
+    __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * TILE; }
+    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { orot[c * TILE] = packed; }
+    __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { out[slot * TILE] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * TILE] = word | (fl << 3); }
     __device__ __forceinline__ void copy(int dst, int src, uint32_t extra) { out[dst * TILE] = out[src * TILE] | (extra << 3); }
 };
@@ -322,7 +391,7 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
                 a = st[i]; b = st[stride + i]; c = st[2 * stride + i]; d = st[3 * stride + i];
             }
             Env e; unpack_env(a, b, c, d, e);
-            TileSink sink{s_out + lid};
+            TileSink sink{s_out + lid, nullptr};
             afterstates_env_impl<true>(e, s_tab, s_scr + tid, ST, L, M, sink);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to the bulk engine
@@ -343,43 +412,54 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
 // integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
 // =================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
                     const uint4 *__restrict__ pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
                     uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    __shared__ CoopSmem cs;
     TPL_SCRATCH;
     load_table(s_tab);
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        Env e; load_env(st, stride, i, e);
-        const uint32_t was = e.state;
-        int k; bool changed;
-        const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
-        if (dlines) dlines[i] = (int8_t)k;
-        if (flags) flags[i] = (uint8_t)fl;
-        if (sto) sto[i] = (int8_t)e.state;
-        acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
-        if (was == S_RUNNING && e.state != S_RUNNING) {
-            acc[0] += 1;
-            if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+    const int ntiles = (n + THREADS - 1) / THREADS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
+        const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
+        if (threadIdx.x == 0) cs.n_items = 0;
+        __syncthreads();
+        if (i < n) {
+            Env e; load_env(st, stride, i, e);
+            const uint32_t was = e.state;
+            int k; bool changed;
+            const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
+            if (dlines) dlines[i] = (int8_t)k;
+            if (flags) flags[i] = (uint8_t)fl;
+            if (sto) sto[i] = (int8_t)e.state;
+            acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
+            if (was == S_RUNNING && e.state != S_RUNNING) {
+                acc[0] += 1;
+                if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+            }
+            if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {            // TPL_RESET_DONE semantics
+                uint32_t ep = episode ? episode[i] + 1u : 1u;
+                if (episode) episode[i] = ep;
+                install_config(e, pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
+                acc[7] += 1;
+                changed = true;
+            }
+            if (changed) {
+                st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+                st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+                st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+            }
+            st[3 * stride + i] = pack_meta(e);
+            GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, nullptr};
+            PendingCtx cx;
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            coop_publish<MODE>(cs, e, cx);
         }
-        if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {            // TPL_RESET_DONE semantics
-            uint32_t ep = episode ? episode[i] + 1u : 1u;
-            if (episode) episode[i] = ep;
-            install_config(e, pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
-            acc[7] += 1;
-            changed = true;
-        }
-        if (changed) {
-            st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
-            st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
-            st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
-        }
-        st[3 * stride + i] = pack_meta(e);
-        GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n};
-        afterstates_env(e, s_tab, scr, THREADS, L, M, sink);
+        __syncthreads();
+        coop_resolve<MODE>(cs, s_tab, scr, base, (uint32_t)n, words, aflags, ff, L);
     }
     if (stats) flush_stats(acc, stats);
 }

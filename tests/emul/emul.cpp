@@ -13,6 +13,7 @@ using namespace tpl;
 static const uint4 *table() { return reinterpret_cast<const uint4 *>(c_orient); }
 
 struct HostSink {
+    static constexpr bool PACKED = false;
     uint32_t *feats; uint8_t *flags; float *ff; size_t n, i;
     void put(int slot, uint32_t word, uint32_t fl) {
         const size_t o = (size_t)slot * n + i;
@@ -25,7 +26,12 @@ struct HostSink {
 
 // sink with copy(): the packed staging the sorted kernel uses (word | flags << 3), one row of 40 per env
 struct PackedRowSink {
+    static constexpr bool PACKED = true;
     uint32_t row[40];
+    int rot;
+    void begin_rotation(int r) { rot = r; }
+    void put_packed_col(int c, uint32_t packed) { row[rot * 10 + c] = packed; }
+    void put_packed(int slot, uint32_t packed) { row[slot] = packed; }
     void put(int slot, uint32_t word, uint32_t fl) { row[slot] = word | (fl << 3); }
     void copy(int dst, int src, uint32_t extra) { row[dst] = row[src] | (extra << 3); }
 };
