@@ -34,8 +34,10 @@ ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out on
 # capture summarised in profiles/r01_ncu_full_v2_afterstates.txt (67.2 MB + 112.7 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
 NCU_TRAFFIC_AFTERSTATES_2P20 = 179.9e6
-NCU_TRAFFIC_FUSED_2P20 = None                 # filled from the fused kernel's capture (profiles/)
-NCU_ALU_PIPE_PCT = 79.4                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, same capture
+# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v4_fused_step_observe.txt):
+# 74.0 MB read + 181.0 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
+NCU_TRAFFIC_FUSED_2P20 = 255.0e6
+NCU_ALU_PIPE_PCT = 73.4                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active (v4 afterstates capture)
 
 
 def load_peaks():

@@ -103,9 +103,10 @@ def select_slots(values: torch.Tensor, flags: torch.Tensor, eps: float, gen) -> 
 
 def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
           config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
-          batch_size: int = BATCH_SIZE, log_every: int = 0) -> tuple:
+          batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True) -> tuple:
     """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
-    Returns (policy_net, TrainStats)."""
+    Returns (policy_net, TrainStats).  The action-selection forward pass over the 40 * num_envs afterstate rows runs
+    under bf16 autocast (it only ranks slots); the optimiser step stays fp32."""
     dev = torch.device(device)
     pool = config_pool if config_pool is not None else synthetic_pool(4096, seed=seed, M=M)
     env = BatchedTetris(num_envs, L, M, device=dev, seed=seed, config_pool=pool)
@@ -122,13 +123,13 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     ar = torch.arange(num_envs, device=dev)
     t_all = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env_ms = 0.0
+    env_events, last_loss = [], None
 
     feats, flags, ff = env.afterstates(f32=True)           # [N,4,10,4] u8 view, [N,4,10] view, [40N,4] f32
     for it in range(iterations):
         eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
-        with torch.no_grad():
-            values = policy_net(ff).view(40, num_envs)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference):
+            values = policy_net(ff).float().view(40, num_envs)
             fl40 = flags.permute(1, 2, 0).reshape(40, num_envs)
             r_slot = reward_from(feats[..., 0].permute(1, 2, 0).reshape(40, num_envs), fl40)
             slot = select_slots(r_slot + GAMMA * values, fl40, eps, gen)
@@ -163,16 +164,19 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
                     for tp_, pp in zip(target_net.parameters(), policy_net.parameters()):
                         tp_.mul_(1 - TAU).add_(pp, alpha=TAU)
                 st.optim_steps += 1
-            st.loss = float(loss.item())
-        torch.cuda.synchronize(dev)
-        env_ms += ev0.elapsed_time(ev1)
+            last_loss = loss.detach()
+        env_events.append((ev0, ev1))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st.eps = eps
         if log_every and (it + 1) % log_every == 0:
             s = env.reduce_stats()
+            st.loss = float(last_loss.item()) if last_loss is not None else float("nan")
             print(f"it {it + 1}: eps {eps:.3f} loss {st.loss:.4f} episodes {s['episodes']} wins {s['wins']} "
                   f"lines/episode {s['lines'] / max(s['episodes'], 1):.2f}")
-    st.env_seconds = env_ms * 1e-3
+    torch.cuda.synchronize(dev)
     st.total_seconds = time.perf_counter() - t_all
+    st.env_seconds = sum(a.elapsed_time(b) for a, b in env_events) * 1e-3
+    st.loss = float(last_loss.item()) if last_loss is not None else float("nan")
     s = env.reduce_stats()
     st.episodes, st.wins = s["episodes"], s["wins"]
     return policy_net, st
