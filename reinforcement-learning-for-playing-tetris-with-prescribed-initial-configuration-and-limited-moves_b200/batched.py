@@ -213,7 +213,7 @@ class BatchedTetris:
         return out
 
     # ------------------------------------------------------------------ afterstates (F)
-    def afterstates(self, f32: bool = False, u8: bool = True, packed: bool = False):
+    def afterstates(self, f32: bool = False, u8: bool = True, packed: bool = False, raw: bool = False):
         """All 40 afterstates of every env: slot (r, c) == clone(env).move(r, c).
 
         Returns (feats, flags[, feats_f32]): ``feats`` uint8 viewed as [N, 4, 10, 4] = (rows cleared, holes,
@@ -222,7 +222,8 @@ class BatchedTetris:
         slot-major row order (row s*N + i), ready to be fed to the value net.
 
         ``packed=True`` is the compact 160 B/env form: only ``feats`` is written and its byte 0 holds
-        ``rows cleared | flags << 3``; returns (feats, None)."""
+        ``rows cleared | flags << 3``; returns (feats, None).  ``raw=True`` returns the slot-major buffers themselves
+        (uint8 [40, N, 4] and [40, N]) instead of the [N, 4, 10, ...] views."""
         n = self.num_envs
         if packed and f32:
             raise ValueError("the packed form has no float output")
@@ -231,6 +232,8 @@ class BatchedTetris:
         ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
         _lib.check(self._L.tpl_afterstates(_ptr(self.state), self.stride, n, _ptr(feats), _ptr(flags), _ptr(ff), self.L, self.M,
                                            self._stream()), "tpl_afterstates")
+        if raw:
+            return (feats, flags, ff) if f32 else (feats, flags)
         fv = feats.view(4, 10, n, 4).permute(2, 0, 1, 3) if feats is not None else None
         gv = flags.view(4, 10, n).permute(2, 0, 1) if flags is not None else None
         return (fv, gv, ff) if f32 else (fv, gv)

@@ -46,29 +46,33 @@ def reward_from(dlines: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
 
 class ReplayMemory:
     """Ring buffer on the device: chosen afterstate (4 x u8), reward, done, and the next state's 40 afterstates
-    (features + flags, u8) for the max in the TD target."""
+    (features + flags, u8) for the max in the TD target.  The 40-slot blocks are kept slot-major ([40, capacity, ...]),
+    the layout the env kernel writes, so a push is 40 contiguous row copies and no transposition."""
 
     def __init__(self, capacity: int, device):
         self.capacity, self.size, self.pos = capacity, 0, 0
         self.x = torch.zeros((capacity, 4), dtype=torch.uint8, device=device)
         self.r = torch.zeros(capacity, dtype=torch.float32, device=device)
         self.done = torch.zeros(capacity, dtype=torch.bool, device=device)
-        self.nx = torch.zeros((capacity, 40, 4), dtype=torch.uint8, device=device)
-        self.nfl = torch.zeros((capacity, 40), dtype=torch.uint8, device=device)
+        self.nx = torch.zeros((40, capacity, 4), dtype=torch.uint8, device=device)
+        self.nfl = torch.zeros((40, capacity), dtype=torch.uint8, device=device)
 
     def push(self, x, r, done, nx, nfl):
-        n = x.shape[0]
-        if n > self.capacity:
-            x, r, done, nx, nfl = x[:self.capacity], r[:self.capacity], done[:self.capacity], nx[:self.capacity], nfl[:self.capacity]
-            n = self.capacity
-        idx = (torch.arange(n, device=x.device) + self.pos) % self.capacity
-        self.x[idx], self.r[idx], self.done[idx], self.nx[idx], self.nfl[idx] = x, r, done, nx, nfl
+        """x [n,4], r [n], done [n], nx [40,n,4], nfl [40,n]."""
+        n = min(x.shape[0], self.capacity)
+        first = min(n, self.capacity - self.pos)
+        for lo, hi, at in ((0, first, self.pos), (first, n, 0)):
+            if hi > lo:
+                k = hi - lo
+                self.x[at:at + k], self.r[at:at + k], self.done[at:at + k] = x[lo:hi], r[lo:hi], done[lo:hi]
+                self.nx[:, at:at + k], self.nfl[:, at:at + k] = nx[:, lo:hi], nfl[:, lo:hi]
         self.pos = (self.pos + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
     def sample(self, batch: int, gen):
+        """-> x [B,4], r [B], done [B], nx [B,40,4], nfl [B,40]"""
         idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
-        return self.x[idx], self.r[idx], self.done[idx], self.nx[idx], self.nfl[idx]
+        return (self.x[idx], self.r[idx], self.done[idx], self.nx[:, idx].permute(1, 0, 2), self.nfl[:, idx].t())
 
 
 @dataclass
@@ -116,7 +120,8 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     policy_net = ValueNet().to(dev)
     target_net = ValueNet().to(dev)
     target_net.load_state_dict(policy_net.state_dict())
-    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True)          # model/train.py:27
+    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True, fused=True)   # model/train.py:27 (fused: one launch)
+    p_params, t_params = list(policy_net.parameters()), list(target_net.parameters())
     loss_fn = nn.SmoothL1Loss()
     memory = ReplayMemory(replay_capacity, dev)
     st = TrainStats()
@@ -125,30 +130,28 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env_events, last_loss = [], None
 
-    feats, flags, ff = env.afterstates(f32=True)           # [N,4,10,4] u8 view, [N,4,10] view, [40N,4] f32
+    feats, flags, ff = env.afterstates(f32=True, raw=True)  # slot-major: [40,N,4] u8, [40,N] u8, [40N,4] f32
     for it in range(iterations):
         eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference):
             values = policy_net(ff).float().view(40, num_envs)
-            fl40 = flags.permute(1, 2, 0).reshape(40, num_envs)
-            r_slot = reward_from(feats[..., 0].permute(1, 2, 0).reshape(40, num_envs), fl40)
-            slot = select_slots(r_slot + GAMMA * values, fl40, eps, gen)
+        with torch.no_grad():
+            slot = select_slots(reward_from(feats[..., 0], flags) + GAMMA * values, flags, eps, gen)
         rot, loc = (slot // 10).to(torch.uint8), (slot % 10).to(torch.uint8)
-        x = feats.reshape(num_envs, 40, 4)[ar, slot].clone()                        # chosen afterstate features
+        x = feats[slot, ar].clone()                                                 # chosen afterstate features [N,4]
         ev0.record()
-        dlines, mflags, state = env.move(rot, loc)
+        # one launch: move -> auto-reset of finished episodes -> afterstates of the new states (tpl_step_observe)
+        dlines, mflags, state, feats, flags, ff = env.step_observe(rot, loc, packed=False, f32=True)
         reward = reward_from(dlines, mflags)
         done = state != 0
-        env.reset(done_only=True)
-        feats, flags, ff = env.afterstates(f32=True)
         ev1.record()
-        memory.push(x, reward, done, feats.reshape(num_envs, 40, 4), flags.reshape(num_envs, 40))
+        memory.push(x, reward, done, feats, flags)
         st.env_steps += num_envs
         if memory.size >= batch_size:
             for _ in range(optim_steps_per_iter):
                 bx, br, bdone, bnx, bnfl = memory.sample(batch_size, gen)
                 with torch.no_grad():
-                    nv = target_net(bnx.view(-1, 4)).view(batch_size, 40)
+                    nv = target_net(bnx.reshape(-1, 4)).view(batch_size, 40)
                     nr = reward_from(bnx[..., 0], bnfl)
                     q = (nr + GAMMA * nv * ((bnfl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
                         (bnfl & (FLAG_ALIAS | FLAG_NOPIECE)) != 0, float("-inf"))
@@ -158,11 +161,11 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
                 loss = loss_fn(policy_net(bx), target)
                 optimizer.zero_grad(set_to_none=True)
                 loss.backward()
-                torch.nn.utils.clip_grad_value_(policy_net.parameters(), 100)
+                torch.nn.utils.clip_grad_value_(p_params, 100, foreach=True)
                 optimizer.step()
-                with torch.no_grad():                                               # soft update, TAU
-                    for tp_, pp in zip(target_net.parameters(), policy_net.parameters()):
-                        tp_.mul_(1 - TAU).add_(pp, alpha=TAU)
+                with torch.no_grad():                                               # soft update, TAU (two foreach launches)
+                    torch._foreach_mul_(t_params, 1 - TAU)
+                    torch._foreach_add_(t_params, p_params, alpha=TAU)
                 st.optim_steps += 1
             last_loss = loss.detach()
         env_events.append((ev0, ev1))

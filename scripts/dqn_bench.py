@@ -7,6 +7,7 @@ import tetris_piclim as tp  # noqa: E402
 from importlib import import_module  # noqa: E402
 train = import_module(tp.__name__ + ".train")
 pool = tp.concat_pools(tp.synthetic_pool(4096, seed=0, M=30), tp.carve_pool(4096, 10, 30, seed0=0, with_solutions=False))
+train.train(num_envs=65536, iterations=5, config_pool=pool, optim_steps_per_iter=4)      # warm-up: cuBLAS / allocator start-up
 net, st = train.train(num_envs=65536, iterations=int(os.environ.get("ITERS", "60")), config_pool=pool, optim_steps_per_iter=4)
 print(json.dumps({"config": "65536 envs, DQN afterstate-value loop, model/train.py constants", "iterations": st.env_steps // 65536,
                   "env_only_steps_per_s": st.env_steps_per_s, "end_to_end_steps_per_s": st.e2e_steps_per_s,
