@@ -250,16 +250,22 @@ def run_b200(args):
     if dist: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
 
-    # the three stand-alone kernels the fused step replaces, CUDA-event timed one by one (explanatory numbers)
-    ksteps = min(K, 20)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(ksteps)]
-    for i in range(ksteps):
-        evs[i][0].record(); env.afterstates(packed=True)
-        evs[i][1].record(); env.move(rot[i], loc[i])
-        evs[i][2].record(); env.reset(done_only=True)
-        evs[i][3].record()
-    torch.cuda.synchronize()
-    k_ms = [sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(ksteps)) / ksteps for j in range(3)]
+    # the three stand-alone kernels the fused step replaces (explanatory numbers): each is launched `reps` times back to
+    # back between two CUDA events, so the ~5 us an event pair adds around a single 25 us launch does not count
+    reps = 10
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for j in range(reps):
+            fn(j)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    env.count_stats = False
+    k_ms = [0.0, 0.0, 0.0]
+    env.reset(); env.rollout_random(8); env.reset(done_only=True)
+    k_ms[0] = timed(lambda j: env.afterstates(packed=True))
+    k_ms[1] = timed(lambda j: env.move(rot[j % total], loc[j % total]))          # 10 moves: most episodes still running
+    k_ms[2] = timed(lambda j: env.reset(done_only=True))                            # first call resets, the rest only scan
 
     # ---- end-to-end through the host-buffer C ABI (pinned host buffers, H2D + D2H inside the timed region) ----
     henv = tp.HostBatchedTetris(n, L_LINES, M_MOVES, device=local, seed=SEED, env_base=rank * n, config_pool=pool)

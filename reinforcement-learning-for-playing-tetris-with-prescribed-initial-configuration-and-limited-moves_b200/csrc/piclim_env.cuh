@@ -103,10 +103,11 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           uint32_t flN, uint32_t flT, bool canon, int w,
                                           int bo0, int bo1, int bo2, int bo3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO01, uint32_t TO23, uint32_t hm, int thr,
-                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, int cmax_warp) {
+                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
     if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
         else { fl |= F_ALIAS; if (!pend) sink.put(r * 10 + C, word, fl); }
+        if (pend) nsmask |= 1u << C;
         return;
     }
     const int y = max(max(H[C] - bo0, H[C + 1] - bo1), max(H[C + 2] - bo2, H[C + 3] - bo3));
@@ -133,7 +134,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             pend = fits ? pnew : pend;
         }
         if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
-        if (!pend) sink.put_packed_col(C, word);
+        if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
     } else {
         wnew = top ? U : wnew;
         const uint32_t fnew = top ? flT : flN;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             pend = fits ? pnew : pend;
         }
         if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
-        if (!pend) sink.put(r * 10 + C, word, fl);
+        if (!pend) sink.put(r * 10 + C, word, fl); else nsmask |= 1u << C;
     }
 }
 
@@ -236,7 +237,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     const uint32_t U = ((agg - cells) << 8) | (bump << 16) | (agg << 24);   // unchanged board (top-out slots)
     const uint32_t K = 0u - ((cells + 4u) << 8);                             // holes' = agg' - (cells + 4)
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
-    unsigned long long pending = 0ull;
+    unsigned long long pending = 0ull, notstored = 0ull;
 
     for (int r = r_begin; r < (UNIFORM ? nrot_warp : r_end); ++r) {
         const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
@@ -249,32 +250,40 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const bool canon = afl == 0u;
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
         const uint32_t Kr = Sink::PACKED ? K + (flN << 3) : K, Ur = Sink::PACKED ? (U | (flT << 3)) : U;
-        uint32_t word = 0, fl = 0, pmask = 0; bool pend = false;
+        uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
         if constexpr (Sink::PACKED) sink.begin_rotation(r);
 #define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, H16, col, A, Bb, agg, Kr, Ur, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
-                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, cmax_warp);
+                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, nsmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         pending |= (unsigned long long)pmask << (10 * r);
+        if constexpr (UNIFORM) notstored |= (unsigned long long)nsmask << (10 * r);
     }
 
     // ---- deferred line-clear slots
     PendingCtx cx{pending, piece, cells, e.lines, fl_noclear};
-    if (defer) { *defer = cx; return; }
-    while (pending) {
-        const int s = __ffsll((long long)pending) - 1;
-        pending &= pending - 1ull;
-        resolve_slot(e.col, cx, s, tab, scr, ss, L, sink);
-    }
+    if (!defer)
+        while (pending) {
+            const int s = __ffsll((long long)pending) - 1;
+            pending &= pending - 1ull;
+            resolve_slot(e.col, cx, s, tab, scr, ss, L, sink);
+        }
 
     if constexpr (UNIFORM) {
-        // rotations >= nrot_warp are aliases for every lane (:61): copy them from rot % n_rot (after the deferred slots)
+        // rotations >= nrot_warp are aliases for every lane (:61): copy them from rot % n_rot.  Slots the fast path
+        // left to the resolver are skipped: resolve_slot stores every alias row of a deferred slot itself.
         const int nrot = orient_nrot(tab[piece * 8]);
         for (int r = nrot_warp; r < 4; ++r)
-            for (int c = 0; c < COLS; ++c) sink.copy(r * 10 + c, (r % nrot) * 10 + c, F_ALIAS);
-        if (nopiece)
+            for (int c = 0; c < COLS; ++c) {
+                const int src = (r % nrot) * 10 + c;
+                if (!defer || !((notstored >> src) & 1ull)) sink.copy(r * 10 + c, src, F_ALIAS);
+            }
+        if (nopiece) {
             for (int s = 0; s < 40; ++s) sink.put(s, 0u, F_NOPIECE);
+            cx.mask = 0ull;
+        }
     }
+    if (defer) *defer = cx;
 }
 
 template <class Sink>

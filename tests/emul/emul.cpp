@@ -38,14 +38,26 @@ struct PackedRowSink {
 
 extern "C" {
 
-// afterstates through the warp-uniform (alias-skipping) variant, each env being its own one-lane "warp"
-int emul_afterstates_uniform(const void *state, int64_t stride, int n, uint8_t *feats_packed, int L, int M) {
+// afterstates through the warp-uniform (alias-skipping) variant, each env being its own one-lane "warp".
+// defer != 0: the row-completing slots are returned by the enumeration and resolved afterwards, the way the
+// CTA-pooled kernels do it.
+int emul_afterstates_uniform(const void *state, int64_t stride, int n, uint8_t *feats_packed, int L, int M, int defer) {
     uint32_t *out = (uint32_t *)feats_packed;
     for (int64_t i = 0; i < n; ++i) {
         Env e; load_env((const uint4 *)state, stride, i, e);
         PackedRowSink sink; for (int s = 0; s < 40; ++s) sink.row[s] = 0xDEADBEEFu;
         uint32_t scr[SCR_ROWS];
-        afterstates_env_impl<true>(e, table(), scr, 1, L, M, sink);
+        if (!defer) {
+            afterstates_env_impl<true>(e, table(), scr, 1, L, M, sink);
+        } else {
+            PendingCtx cx;
+            afterstates_env_impl<true>(e, table(), scr, 1, L, M, sink, 0, 4, &cx);
+            unsigned long long m = cx.mask;
+            while (m) {
+                const int s = __builtin_ffsll((long long)m) - 1; m &= m - 1ull;
+                resolve_slot(e.col, cx, s, table(), scr, 1, L, sink);
+            }
+        }
         for (int s = 0; s < 40; ++s) out[(size_t)s * n + i] = sink.row[s];
     }
     return 0;

@@ -44,7 +44,7 @@ class EmulEngine:
             "reset_from_pool": [P, I64, I, P, I, P, P, I, P, U64, U64, I],
             "step": [P, I64, I, P, P, P, P, P, I, I],
             "afterstates": [P, I64, I, P, P, P, I, I],
-            "afterstates_uniform": [P, I64, I, P, I, I],
+            "afterstates_uniform": [P, I64, I, P, I, I, I],
             "afterstates_split": [P, I64, I, P, I, I],
             "gen_pieces": [P, I, I, U64, U64, P, U32],
             "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, U64, U64, I, P, P, P, I, I],
@@ -114,9 +114,10 @@ class EmulEngine:
     def afterstates_packed(self, s, L, M):
         feats = np.zeros((40, s.n, 4), np.uint8)
         self.L.emul_afterstates(_np_ptr(s.planes), s.stride, s.n, _np_ptr(feats), None, None, L, M)
-        uni = np.zeros((40, s.n, 4), np.uint8)          # the alias-skipping variant must give the same bytes
-        self.L.emul_afterstates_uniform(_np_ptr(s.planes), s.stride, s.n, _np_ptr(uni), L, M)
-        assert np.array_equal(uni, feats), "warp-uniform afterstate variant differs from the plain one"
+        for defer in (0, 1):                            # the alias-skipping variant must give the same bytes
+            uni = np.zeros((40, s.n, 4), np.uint8)
+            self.L.emul_afterstates_uniform(_np_ptr(s.planes), s.stride, s.n, _np_ptr(uni), L, M, defer)
+            assert np.array_equal(uni, feats), f"warp-uniform afterstate variant (defer={defer}) differs from the plain one"
         spl = np.full((40, s.n, 4), 0xEE, np.uint8)     # and so must the one-thread-per-rotation variant
         self.L.emul_afterstates_split(_np_ptr(s.planes), s.stride, s.n, _np_ptr(spl), L, M)
         assert np.array_equal(spl, feats), "rotation-split afterstate variant differs from the plain one"
