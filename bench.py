@@ -210,6 +210,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
