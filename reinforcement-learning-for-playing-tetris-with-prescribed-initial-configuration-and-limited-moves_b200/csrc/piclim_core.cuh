@@ -38,9 +38,9 @@ enum : uint32_t { S_RUNNING = 0, S_WON = 1, S_LOST = 2 };
 //        bits 16-18 w, bits 20-22 h, bits 24-25 n_rot-1, bit 28 = rot is an alias (rot >= n_rot)
 //   a.y: bo bytes: byte j = rows between the shape's bottom row and the lowest cell of column j
 //        (= h-1-profile[j] with profile the tuple at :25-55); 64 for j >= w so it never wins the max
-//   a.z: (to0, to1) as s16x2, to_j = (height of the highest cell of column j above the bottom row) + 1,
+//   a.z: (to0, to2) as s16x2, to_j = (height of the highest cell of column j above the bottom row) + 1,
 //        -64 for j >= w so that max(H_j, y + to_j) leaves the column height alone
-//   a.w: (to2, to3) as s16x2
+//   a.w: (to1, to3) as s16x2   (even/odd pairing: the four new heights then pack into bytes with one multiply-add)
 //   b.x: bo nibbles (4 bits per column, no sentinel) -- used by the column-aligned general path
 //   b.y: (1 << h) - 1      b.z: 20 - h (top-out iff y > 20 - h)      b.w: unused
 // ---------------------------------------------------------------------------------------------
@@ -67,7 +67,7 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
         to[j] = (uint32_t)(h - highest);
     }
     return OrientEntry{cb | ((uint32_t)w << 16) | ((uint32_t)h << 20) | ((uint32_t)(nrot - 1) << 24) | (alias ? 1u << 28 : 0u),
-                       bo, to[0] | (to[1] << 16), to[2] | (to[3] << 16),
+                       bo, to[0] | (to[2] << 16), to[1] | (to[3] << 16),
                        bon, (1u << h) - 1u, (uint32_t)(20 - h), 0u};
 }
 
@@ -152,6 +152,17 @@ __device__ __forceinline__ int col_height(uint32_t c) {
     int r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(c));
     return r + 1;
+#endif
+}
+
+// a * b + c pinned to the FMA pipe (IMAD), e.g. to pack bytes with `hi * 256 + lo` instead of an ALU-pipe PRMT/LEA
+__device__ __forceinline__ uint32_t mad_fma_pipe(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef TPL_HOST_EMUL
+    return a * b + c;
+#else
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
 #endif
 }
 

@@ -89,7 +89,8 @@ __host__ __device__ constexpr uint32_t sel_y(int c) {
 // sum over the window pairs (H[c-1],n0),(n0,n1),(n1,n2),(n2,n3),(n3,H[c+4]) restricted to columns 0..9
 template <int C>
 __device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, uint32_t hnext, uint32_t acc) {
-    const uint32_t X = __byte_perm(N4, hprev, sel_x(C));
+    // X = (H[c-1], n0, n1, n2): for the interior columns that is N4 * 256 + H[c-1], one IMAD on the FMA pipe
+    const uint32_t X = (C >= 1 && C <= 7) ? mad_fma_pipe(N4, 256u, hprev) : __byte_perm(N4, hprev, sel_x(C));
     const uint32_t Y = (C <= 6) ? N4 : __byte_perm(N4, 0u, sel_y(C));
     uint32_t s = __vsadu4(X, Y) + acc;
     if (C + 4 <= 9) s = __sad((int)(N4 >> 24), (int)hnext, s);
@@ -116,9 +117,9 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & (col[C] | mul_fma_pipe(cb0, pw)) & (col[C + 1] | mul_fma_pipe(cb1, pw)) &
                           (col[C + 2] | mul_fma_pipe(cb2, pw)) & (col[C + 3] | mul_fma_pipe(cb3, pw));
     const uint32_t Y2 = (uint32_t)y * 0x10001u;
-    const uint32_t N01 = __viaddmax_s16x2(Y2, TO01, H16[C]);          // H16[c] = (H[c], H[c+1]) as s16x2
-    const uint32_t N23 = __viaddmax_s16x2(Y2, TO23, H16[C + 2]);
-    const uint32_t N4 = __byte_perm(N01, N23, 0x6420);
+    const uint32_t N02 = __viaddmax_s16x2(Y2, TO01, H16[C]);          // H16[c] = (H[c], H[c+2]) as s16x2; TO01 = (to0, to2)
+    const uint32_t N13 = __viaddmax_s16x2(Y2, TO23, H16[C + 1]);      // TO23 = (to1, to3)
+    const uint32_t N4 = mad_fma_pipe(N13, 256u, N02);                 // bytes (n0, n1, n2, n3)
     const uint32_t agg2 = __vsadu4(N4, Hw[C]) + agg;
     const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
     uint32_t wnew = agg2 * 0x01000100u + K;
@@ -213,9 +214,9 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     Hw[1] = __byte_perm(HB0, HB1, 0x4321); Hw[2] = __byte_perm(HB0, HB1, 0x5432); Hw[3] = __byte_perm(HB0, HB1, 0x6543);
     Hw[5] = __byte_perm(HB1, HB2, 0x4321); Hw[6] = __byte_perm(HB1, HB2, 0x5432); Hw[7] = __byte_perm(HB1, HB2, 0x6543);
     Hw[9] = HB2 >> 8;
-    uint32_t H16[12];                                // H16[c] = (H[c], H[c+1]) as s16x2, zero beyond column 9
+    uint32_t H16[12];                                // H16[c] = (H[c], H[c+2]) as s16x2, zero beyond column 9
 #pragma unroll
-    for (int c = 0; c < 12; ++c) H16[c] = (uint32_t)H[c] | ((uint32_t)H[c + 1] << 16);
+    for (int c = 0; c < 12; ++c) H16[c] = (uint32_t)H[c] | ((uint32_t)H[c + 2] << 16);
     const uint32_t agg = __vsadu4(HB0, 0u) + __vsadu4(HB1, 0u) + __vsadu4(HB2, 0u);
     const uint32_t bump = __vsadu4(Hw[0], Hw[1]) + __vsadu4(Hw[4], Hw[5]) + (uint32_t)__sad(H[8], H[9], 0u);
     uint32_t Bb[COLS];                               // bump minus the pairs a placement at c can change

@@ -169,7 +169,11 @@ struct GlobalSink {
     uint32_t n;
     uint32_t *wrot;                                   // row of the current rotation's column 0
     __device__ __forceinline__ void begin_rotation(int r) { wrot = words + (size_t)((uint32_t)(r * 10) * n); }
-    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { wrot[(uint32_t)c * n] = packed; }
+    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) {
+        uint64_t addr;                                // wrot + c * n words, as ONE IMAD.WIDE on the FMA pipe (not an ALU LEA pair)
+        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"((uint32_t)c * n), "l"(wrot));
+        *reinterpret_cast<uint32_t *>(addr) = packed;
+    }
     __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { words[(uint32_t)slot * n] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
         const uint32_t o = (uint32_t)slot * n;
