@@ -34,10 +34,11 @@ ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out on
 # capture summarised in profiles/r01_ncu_full_v2_afterstates.txt (67.2 MB + 112.7 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
 NCU_TRAFFIC_AFTERSTATES_2P20 = 179.9e6
-# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v4_fused_step_observe.txt):
-# 74.0 MB read + 181.0 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
-NCU_TRAFFIC_FUSED_2P20 = 255.0e6
-NCU_ALU_PIPE_PCT = 73.4                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active (v4 afterstates capture)
+# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v5_fused_step_observe.txt):
+# 74.0 MB read + 183.1 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
+NCU_TRAFFIC_FUSED_2P20 = 257.1e6
+NCU_ALU_PIPE_PCT = 61.7                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v5 capture)
+NCU_ALU_PIPE_PCT_AFTERSTATES = 72.2           # same metric, stand-alone afterstates_kernel<0> (profiles/r01_ncu_full_v5_afterstates_step.txt)
 
 
 def load_peaks():
@@ -311,7 +312,9 @@ def run_b200(args):
                      "traffic": NCU_TRAFFIC_FUSED_2P20 if n == (1 << 20) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_FUSED * n, "avg_launch_ms": fused_ms,
                      "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT,
-                                      "note": "the kernel is ALU-pipe-bound, not HBM-bound (DESIGN.md section 3)"}},
+                                      "afterstates_kernel_alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT_AFTERSTATES,
+                                      "note": "the enumeration is integer(ALU)-pipe-bound, not HBM-bound (DESIGN.md section 3); "
+                                              "percentages are ncu sm__inst_executed_pipe_alu of peak, captures under profiles/"}},
         "kernels": {
             "note": "stand-alone kernels (3 launches per step); their sum is what the fused step replaces",
             "afterstates": {"ms": k_ms[0], "afterstates_per_s": n * 40 / (k_ms[0] * 1e-3), "GBps": as_gbs,

@@ -131,11 +131,19 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
     TPL_SCRATCH;
     load_table(s_tab);
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        Env e; load_env(st, stride, i, e);
+    // software pipeline: the next env's record and action are in flight while the current move is computed
+    const int64_t stepn = (int64_t)gridDim.x * THREADS;
+    int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a, d = a; uint32_t ar = 0, al = 0;
+    if (i < n) { a = st[i]; b = st[stride + i]; c = st[2 * stride + i]; d = st[3 * stride + i]; ar = rot[i]; al = loc[i]; }
+    for (; i < n; i += stepn) {
+        const int64_t i2 = i + stepn;
+        uint4 na = a, nb = b, nc = c, nd = d; uint32_t nr = 0, nl = 0;
+        if (i2 < n) { na = st[i2]; nb = st[stride + i2]; nc = st[2 * stride + i2]; nd = st[3 * stride + i2]; nr = rot[i2]; nl = loc[i2]; }
+        Env e; unpack_env(a, b, c, d, e);
         const uint32_t was = e.state;
         int k; bool changed;
-        const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
+        const uint32_t fl = step_env(e, s_tab, scr, THREADS, ar, al, L, M, k, changed);
         if (changed) {
             st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
             st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
@@ -150,6 +158,7 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
             acc[0] += 1;
             if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
         }
+        a = na; b = nb; c = nc; d = nd; ar = nr; al = nl;
     }
     if (stats) flush_stats(acc, stats);
 }
@@ -592,7 +601,11 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step: plane_stride < n");
     if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step: L/M out of range");
     if (n == 0) return 0;
-    step_kernel<<<grid_persistent(n, 16), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
+    static int step_blocks_per_sm = 0;                 // exactly one resident wave: no partial second wave at the tail
+    if (!step_blocks_per_sm &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&step_blocks_per_sm, step_kernel, THREADS, 0) != cudaSuccess || step_blocks_per_sm <= 0))
+        step_blocks_per_sm = 8;
+    step_kernel<<<grid_persistent(n, step_blocks_per_sm), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
                                                                     (unsigned long long *)stats, L, M);
     return check_launch("tpl_step");
 }
