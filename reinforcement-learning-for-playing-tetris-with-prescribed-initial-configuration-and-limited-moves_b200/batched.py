@@ -251,7 +251,7 @@ class BatchedTetris:
             raise ValueError("the packed form has no float output")
         d_rot, d_loc = self._dev(rot, torch.uint8, (n,)), self._dev(loc, torch.uint8, (n,))
         dl, fl, st = self._buf("dlines", (n,), torch.int8), self._buf("mflags", (n,), torch.uint8), self._buf("mstate", (n,), torch.int8)
-        feats = self._buf("feats", (40, n, 4), torch.uint8) if not (f32 and not packed and False) else None
+        feats = self._buf("feats", (40, n, 4), torch.uint8)
         aflags = None if packed else self._buf("aflags", (40, n), torch.uint8)
         ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
         _lib.check(self._L.tpl_step_observe(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
