@@ -107,7 +107,7 @@ def select_slots(values: torch.Tensor, flags: torch.Tensor, eps: float, gen) -> 
 
 def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
           config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
-          batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True) -> tuple:
+          batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True, log_fn=None) -> tuple:
     """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
     Returns (policy_net, TrainStats).  The action-selection forward pass over the 40 * num_envs afterstate rows runs
     under bf16 autocast (it only ranks slots); the optimiser step stays fp32."""
@@ -128,7 +128,7 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     ar = torch.arange(num_envs, device=dev)
     t_all = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env_events, last_loss = [], None
+    env_events, last_loss, prev_stats = [], None, {}
 
     feats, flags, ff = env.afterstates(f32=True, raw=True)  # slot-major: [40,N,4] u8, [40,N] u8, [40N,4] f32
     for it in range(iterations):
@@ -174,6 +174,10 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
         if log_every and (it + 1) % log_every == 0:
             s = env.reduce_stats()
             st.loss = float(last_loss.item()) if last_loss is not None else float("nan")
+            if log_fn is not None:
+                log_fn(it + 1, eps, st.loss, s, prev_stats)
+                prev_stats = dict(s)
+                continue
             print(f"it {it + 1}: eps {eps:.3f} loss {st.loss:.4f} episodes {s['episodes']} wins {s['wins']} "
                   f"lines/episode {s['lines'] / max(s['episodes'], 1):.2f}")
     torch.cuda.synchronize(dev)
