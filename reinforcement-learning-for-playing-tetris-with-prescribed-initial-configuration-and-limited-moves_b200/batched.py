@@ -44,7 +44,7 @@ class BatchedTetris:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs, self.L, self.M = int(num_envs), int(L), int(M)
-        self.seed, self.env_base, self.gen_pieces = int(seed), int(env_base), int(gen_pieces)
+        self.seed, self.env_base, self.gen_count = int(seed), int(env_base), int(gen_pieces)
         self.stride = (self.num_envs + 31) // 32 * 32
         with torch.cuda.device(self.device):
             self.state = torch.zeros((4, self.stride, 4), dtype=torch.int32, device=self.device)
@@ -128,7 +128,7 @@ class BatchedTetris:
             (self.tstep.zero_() if d_mask is None else self.tstep.masked_fill_(d_mask.bool(), 0))
         _lib.check(self._L.tpl_reset_from_pool(_ptr(self.state), self.stride, n, _ptr(self.pool), self.pool_size,
                                                _ptr(d_idx), _ptr(d_mask), mode, _ptr(self.episode), self.seed,
-                                               self.env_base, self.gen_pieces, self._stream()), "tpl_reset_from_pool")
+                                               self.env_base, self.gen_count, self._stream()), "tpl_reset_from_pool")
 
     def load(self, boards, pieces, npieces=None, lines=None, moves=None, state=None, head=None) -> None:
         """Install explicit env states (boundary format).  Optional counters let tests resume mid-episode."""
@@ -257,7 +257,7 @@ class BatchedTetris:
         _lib.check(self._L.tpl_step_observe(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
                                             _ptr(self.stats) if self.count_stats else None,
                                             _ptr(self.pool) if auto_reset else None, self.pool_size, _ptr(self.episode), self.seed,
-                                            self.env_base, self.gen_pieces, _ptr(feats), _ptr(aflags), _ptr(ff), self.L, self.M,
+                                            self.env_base, self.gen_count, _ptr(feats), _ptr(aflags), _ptr(ff), self.L, self.M,
                                             self._stream()), "tpl_step_observe")
         return dl, fl, st, feats, aflags, ff
 
@@ -272,7 +272,7 @@ class BatchedTetris:
         self._need_pool()
         _lib.check(self._L.tpl_rollout_random(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
                                               _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps), self.seed,
-                                              self.env_base, self.gen_pieces, self.L, self.M, self._stream()), "tpl_rollout_random")
+                                              self.env_base, self.gen_count, self.L, self.M, self._stream()), "tpl_rollout_random")
 
     def rollout_greedy(self, steps: int, weights: Sequence[int]) -> None:
         """``steps`` greedy moves per env: arg-max over the 40 afterstates of the integer linear value
@@ -281,7 +281,7 @@ class BatchedTetris:
         w = (ctypes.c_int32 * 6)(*[int(x) for x in weights])
         _lib.check(self._L.tpl_rollout_greedy(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
                                               _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps),
-                                              ctypes.cast(w, ctypes.c_void_p), self.seed, self.env_base, self.gen_pieces,
+                                              ctypes.cast(w, ctypes.c_void_p), self.seed, self.env_base, self.gen_count,
                                               self.L, self.M, self._stream()), "tpl_rollout_greedy")
 
     def gen_pieces(self, count: int, episode: int = 0) -> torch.Tensor:

@@ -100,6 +100,9 @@ def test_batched_api_vs_oracle(tp, carve_pool):
         env.move(np.zeros(n), np.full(n, -1))
     with pytest.raises(ValueError):
         env.move(np.zeros(n + 1), np.zeros(n + 1))
+    # counter-based 7-bag sequences through the batched API
+    from oracle import c_oracle as co
+    assert np.array_equal(env.gen_pieces(31, episode=4).cpu().numpy(), co.gen_pieces(21, 1000, n, 4, 31))
     # explicit boards reset + done_only auto-reset
     env.reset(done_only=True)
     f = env.fields()
@@ -207,3 +210,13 @@ def test_full_size_properties(tp):
     b.rollout_random(13)
     assert torch.equal(a.state, b.state) and torch.equal(a.stats, b.stats) and torch.equal(a.episode, b.episode)
     assert int(a.stats[6]) == 13 * n
+
+
+def test_all_entry_points_on_ragged_sizes(tp):
+    """Every kernel and API layer once on n = 1, 33, 1000, 40 000 (split kernel, tile kernels, ragged tails).
+    (compute-sanitizer is closed on this GPU pool; this is the bounds smoke that remains, next to the parity tests.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sanitize case done" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
