@@ -172,8 +172,9 @@ int tpl_env_get_state(tpl_env *e, uint16_t *rows, uint8_t *cur, uint8_t *next, i
                       int8_t *st, uint8_t *head, uint8_t *npieces, uint8_t *queue);
 /* afterstates to host: feats u8[40][n][4], flags u8[40][n] */
 int tpl_env_afterstates(tpl_env *e, uint8_t *feats, uint8_t *flags);
-/* one fused host-facing rollout step: H2D actions -> move -> auto-reset of finished envs -> afterstates of the
- * new states -> D2H (dlines, flags, st, feats, aflags).  This is the call bench.py's e2e figure times. */
+/* one host-facing rollout step: H2D actions -> tpl_step_observe (move -> auto-reset of finished envs -> afterstates of
+ * the new states, one kernel) -> D2H (dlines, flags, st, feats[, aflags]).  aflags == NULL selects the compact form
+ * (feats byte 0 = rows cleared | flags << 3).  This is the call bench.py's e2e figure times. */
 int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
                          int8_t *st, uint8_t *feats, uint8_t *aflags);
 /* pinned (page-locked) host buffers so the copies inside the calls above are true async DMA */
