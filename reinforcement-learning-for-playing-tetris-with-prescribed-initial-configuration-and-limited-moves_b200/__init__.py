@@ -6,7 +6,7 @@ from .configs import ConfigPool, carve_pool, concat_pools, gen_pieces, load_pool
 from . import build  # noqa: F401
 from ._lib import TplError, launch_count  # noqa: F401
 from .host_env import HostBatchedTetris, PinnedArray  # noqa: F401
-from .tetris import Tetris, get_tetromino, tetrominos  # noqa: F401
+from .tetris import RandomPieceGenerator, Tetris, get_tetromino, tetrominos  # noqa: F401
 
 
 def __getattr__(name):          # torch is only imported when the device-tensor API is asked for

@@ -123,6 +123,56 @@ def synthetic_pool(K: int, seed: int = 0, M: int = 30, max_height: int = 12, fil
     return ConfigPool(rows, pieces, np.full(K, M + 1, np.uint8))
 
 
+_carve_lib = None
+
+
+def _carve():
+    global _carve_lib
+    if _carve_lib is None:
+        import ctypes
+        from . import build as _build
+        lib = ctypes.CDLL(_build.build_carve())
+        V = ctypes.c_void_p
+        lib.carve_generate.restype = ctypes.c_int
+        lib.carve_generate.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, V, V, ctypes.c_int, V, V, V, ctypes.c_int]
+        lib.carve_generate_from_state.restype = ctypes.c_int
+        lib.carve_generate_from_state.argtypes = [V, ctypes.c_int, ctypes.c_int, V, V, ctypes.c_int, V, V, V]
+        lib.carve_apply.restype = ctypes.c_int
+        lib.carve_apply.argtypes = [V, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _carve_lib = lib
+    return _carve_lib
+
+
+def carve_one_from_global_random(L: int, M: int):
+    """One prescribed config drawn from Python's GLOBAL ``random`` stream exactly as the reference's
+    ``Tetris(L, M, warm_reset=False)`` draws it (``game/tetris.py:226-284``): the MT19937 state is handed to the native
+    generator and the advanced state is put back, so ``random.seed(k)`` before the call reproduces the reference's
+    board, pieces and solution, and later ``random`` calls continue where the reference's would.
+    Returns (rows uint16[20], pieces list[int], solution list[(rot, loc)])."""
+    import ctypes
+    import random
+    ver, internal, gauss = random.getstate()
+    st = np.array(internal, dtype=np.uint32)                      # 624 words + index
+    rows = np.zeros(20, np.uint16)
+    pieces = np.zeros(max(M + 1, 1), np.uint8)
+    npieces, nsol = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    sol = np.full((max(M, 1), 2), -1, np.int8)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)                  # noqa: E731
+    if _carve().carve_generate_from_state(p(st), L, M, p(rows), p(pieces), len(pieces), p(npieces), p(sol), p(nsol)) != 0:
+        raise ValueError("native carve generator rejected its arguments (1 <= L <= 16, M >= 1)")
+    random.setstate((ver, tuple(int(x) for x in st), gauss))
+    return rows, [int(x) for x in pieces[:int(npieces[0])]], [(int(r), int(c)) for r, c in sol[:int(nsol[0])]]
+
+
+def carve_apply(rows: np.ndarray, piece: int, rotations: int, location: int, allow_partial: bool) -> bool:
+    """``Tetris.carve`` (``game/tetris.py:286-311``) on uint16[20] bitrows, in place."""
+    import ctypes
+    rc = _carve().carve_apply(ctypes.c_void_p(rows.ctypes.data), int(piece), int(rotations), int(location), int(bool(allow_partial)))
+    if rc < 0:
+        raise ValueError("carve: piece/location out of range")
+    return rc == 1
+
+
 def carve_pool(K: int, L: int, M: int, seed0: int = 0, threads: Optional[int] = None, with_solutions: bool = True) -> ConfigPool:
     """K prescribed configs from the native carving generator (csrc/carve_gen.cpp): config k is exactly what the
     reference produces for random.seed(seed0 + k); Tetris(L, M, warm_reset=False, debug=True)

@@ -134,9 +134,8 @@ bool carve(Board &b, int piece, int rot, int loc, bool allow_partial) {
 struct Checkpoint { Board board; std::vector<int> pieces; std::vector<std::pair<int, int>> solution; };
 
 // Tetris._generate_initial_config (:226-284).  pieces/solution are kept in play order (index 0 = first piece).
-void generate(uint64_t seed, int L, int M, uint16_t *rows_out, uint8_t *pieces_out, int *npieces_out,
+void generate(PyRandom &rng, int L, int M, uint16_t *rows_out, uint8_t *pieces_out, int *npieces_out,
               int8_t *solution_out /* [M][2] or null */, int *nsol_out) {
-    PyRandom rng; rng.seed(seed);
     Board b; std::memset(b.r, 0, sizeof(b.r));
     for (int i = 20 - L; i < 20; ++i) b.r[i] = 0x3FF;                                  // :228
     std::vector<int> bag;                                                              // RandomPieceGenerator.pieces
@@ -206,7 +205,8 @@ int carve_generate(uint64_t seed0, int count, int L, int M, uint16_t *rows, uint
     auto work = [&](int t) {
         for (int k = t; k < count; k += nthreads) {
             int np = 0, ns = 0;
-            generate(seed0 + (uint64_t)k, L, M, rows + (size_t)k * 20, pieces + (size_t)k * pieces_stride, &np,
+            PyRandom rng; rng.seed(seed0 + (uint64_t)k);
+            generate(rng, L, M, rows + (size_t)k * 20, pieces + (size_t)k * pieces_stride, &np,
                      solutions ? solutions + (size_t)k * M * 2 : nullptr, &ns);
             npieces[k] = (uint8_t)np;
             if (nsol) nsol[k] = (uint8_t)ns;
@@ -217,6 +217,35 @@ int carve_generate(uint64_t seed0, int count, int L, int M, uint16_t *rows, uint
     work(0);
     for (auto &x : th) x.join();
     return 0;
+}
+
+// One config drawn from a caller-supplied MT19937 state (CPython's random.getstate()[1]: 624 words + index) which is
+// advanced in place: lets the Python facade consume the GLOBAL `random` stream exactly like the reference's
+// Tetris(L, M, warm_reset=False) does, so code that seeds `random` gets the reference's configs and stream position.
+int carve_generate_from_state(uint32_t *mt625, int L, int M, uint16_t *rows, uint8_t *pieces, int pieces_stride, uint8_t *npieces,
+                              int8_t *solution, uint8_t *nsol) {
+    if (!mt625 || L < 1 || L > 16 || M < 1 || pieces_stride < M + 1 || !rows || !pieces || !npieces) return -1;
+    PyRandom rng;
+    std::memcpy(rng.mt, mt625, sizeof(rng.mt));
+    rng.idx = (int)mt625[624];
+    int np = 0, ns = 0;
+    generate(rng, L, M, rows, pieces, &np, solution, &ns);
+    *npieces = (uint8_t)np;
+    if (nsol) *nsol = (uint8_t)ns;
+    std::memcpy(mt625, rng.mt, sizeof(rng.mt));
+    mt625[624] = (uint32_t)rng.idx;
+    return 0;
+}
+
+// Tetris.carve (:286-311) on a bitrow board, in place.  Returns 1 if the piece was carved, 0 if not, -1 on bad arguments.
+int carve_apply(uint16_t *rows, int piece, int rot, int loc, int allow_partial) {
+    if (!rows || piece < 0 || piece > 6 || loc < 0) return -1;
+    const Shape s = make_shape(piece, ((rot % 4) + 4) % 4);
+    if (loc + s.w > 10) return -1;
+    Board b; std::memcpy(b.r, rows, sizeof(b.r));
+    const bool ok = carve(b, piece, ((rot % 4) + 4) % 4, loc, allow_partial != 0);
+    std::memcpy(rows, b.r, sizeof(b.r));
+    return ok ? 1 : 0;
 }
 
 // the first n outputs of random.seed(seed); [random.randint(0, hi) ...]  (lets the tests pin the RNG restatement)

@@ -8,11 +8,14 @@ when ``debug``) -- the callers at ``game/main.py:49-57``, ``game/performance_tes
 host-buffer C ABI (a 1-env batch): the host attributes are uploaded, ``tpl_env_move`` runs, the result is read
 back.  This is the parity/drop-in tool; throughput lives in ``BatchedTetris``.
 
-Differences, all outside the hot path:
-  * reset points come from a prescribed-config pool (``config_pool=``; default: the synthetic pool of
-    ``configs.synthetic_pool``) instead of the carve / forward generators (``game/tetris.py:226-352``,
-    ``game/tetris_algo_main``), which are out of scope; ``warm_reset`` is accepted and ignored (no processes).
-  * ``render=True`` is not supported (pygame UI, out of scope).
+Reset points: by default they come from the native carving generator (``csrc/carve_gen.cpp``) fed with Python's
+GLOBAL ``random`` state, so ``random.seed(k); Tetris(L, M, warm_reset=False, debug=True)`` yields the reference's
+board, pieces and ``solution`` for that seed and leaves ``random`` where the reference would (``game/tetris.py:226-284``);
+``carve``, ``calculate_drop(_deltas)`` and ``RandomPieceGenerator`` are provided with the reference's signatures, so the
+reference's own test file (``game/main.py``) runs against this module.  ``config_pool=`` switches to drawing from a
+pool with the counter RNG instead.  Differences, all outside the hot path: ``warm_reset=True``
+starts no worker processes (configs are generated on demand, in microseconds-to-milliseconds); the forward generator
+(``game/tetris_algo_main``) is not included; ``render=True`` is not supported (pygame UI).
 Like the reference, ``reset()`` does NOT zero ``lines_cleared``/``moves_used``/``state`` (``:438-443``; only
 the constructor does, ``:149-151``); pass ``fresh=True`` to get an RL-style reset.
 """
@@ -20,9 +23,12 @@ from __future__ import annotations
 
 from typing import Optional
 
+import random
+
 import numpy as np
 
-from .configs import ConfigPool, bool_from_rows, rng_words, rows_from_bool, synthetic_pool, STREAM_CONFIG, MAX_PIECES
+from .configs import (ConfigPool, bool_from_rows, carve_apply, carve_one_from_global_random, rng_words, rows_from_bool,
+                      STREAM_CONFIG, MAX_PIECES)
 from .host_env import HostBatchedTetris
 
 _ROW_MASKS = (
@@ -56,6 +62,47 @@ def _state_to_code(state) -> int:
     return 0 if state is None else (1 if state else 2)
 
 
+class RandomPieceGenerator:
+    """7-bag piece source with the reference's interface (``game/tetris.py:64-108``), on the global ``random`` stream:
+    ``get_random_piece() -> ((piece, index), regenerated)`` draws without removing (``delete_index`` removes),
+    ``get_random_sequence(n)`` concatenates shuffled bags, starting with whatever is left of the current one."""
+
+    def __init__(self) -> None:
+        self.pieces = []
+
+    def generate_pieces(self) -> None:
+        self.pieces = list(range(7))
+
+    def _refill(self) -> bool:
+        if self.pieces:
+            return False
+        self.generate_pieces()
+        return True
+
+    def get_random_piece(self):
+        regenerated = self._refill()
+        index = random.randint(0, len(self.pieces) - 1)
+        return (self.pieces[index], index), regenerated
+
+    def delete_index(self, index) -> None:
+        del self.pieces[index]
+
+    def get_random_sequence(self, length: int):
+        out = []
+        while len(out) < length:
+            self._refill()
+            random.shuffle(self.pieces)
+            out.extend(self.pieces[:min(length - len(out), 7)])
+            self.pieces = []
+        return out
+
+    def reset(self) -> None:
+        self.pieces.clear()
+
+    def __len__(self) -> int:
+        return len(self.pieces)
+
+
 class Tetris:
     def __init__(self, L: int, M: int, warm_reset: bool = True, render: bool = False, framerate: int = 30,
                  debug: bool = False, *, config_pool: Optional[ConfigPool] = None, seed: int = 0, device: int = 0):
@@ -70,13 +117,21 @@ class Tetris:
         self.debug = debug
         if debug:
             self.solution = []
+        self.random_piece_generator = RandomPieceGenerator()
         self.board = np.full((20, 10), False, dtype=bool)
         self.pieces = []
         self._seed = seed
+        self._device = device
         self._episode = 0
-        self._pool = config_pool if config_pool is not None else synthetic_pool(256, seed, min(M, MAX_PIECES - 1))
-        self._env = HostBatchedTetris(1, L, M, device=device, seed=seed)
+        self._pool = config_pool
+        self._env_handle = None                 # the CUDA handle is created by the first call that needs the GPU
         self.load_warm_reset()
+
+    @property
+    def _env(self) -> HostBatchedTetris:
+        if self._env_handle is None:
+            self._env_handle = HostBatchedTetris(1, self.L, self.M, device=self._device, seed=self._seed)
+        return self._env_handle
 
     # -- reset (game/tetris.py:438-449) ---------------------------------------------------------------
     def reset(self, fresh: bool = False) -> None:
@@ -87,6 +142,9 @@ class Tetris:
         self.load_warm_reset()
 
     def load_warm_reset(self) -> None:
+        if self._pool is None:                  # the reference's own generator, on the global `random` stream
+            self._generate_initial_config()
+            return
         w0 = rng_words(self._seed, np.array([0], np.uint64), self._episode, STREAM_CONFIG, 0)[0]
         k = int((int(w0[0]) * self._pool.K) >> 32)
         self._episode += 1
@@ -95,6 +153,30 @@ class Tetris:
         if self.debug:
             sol = self._pool.solutions
             self.solution = ([(int(r), int(c)) for r, c in sol[k, :int(self._pool.nsol[k])]] if sol is not None else [])
+
+    # -- carving generator (game/tetris.py:226-352), native, bit-identical to the reference -----------------
+    def _generate_initial_config(self) -> None:
+        rows, pieces, solution = carve_one_from_global_random(self.L, self.M)
+        self.board = bool_from_rows(rows)
+        self.pieces = pieces
+        if self.debug:
+            self.solution = solution
+
+    def carve(self, piece: int, rotations: int, location: int, allow_partial: bool) -> bool:
+        rows = rows_from_bool(self.board)
+        ok = carve_apply(rows, piece, rotations, location, allow_partial)
+        if ok:
+            self.board[:, :] = bool_from_rows(rows)
+        return ok
+
+    def calculate_drop_deltas(self, location, reverse_tetromino_topography, tetromino_width):
+        """Column tops (first filled row from the top, else 20) minus the shape's bottom profile (:427-433)."""
+        cols = self.board[:, location:location + tetromino_width]
+        tops = np.where(cols.any(axis=0), cols.argmax(axis=0), 20)
+        return tops - np.asarray(reverse_tetromino_topography)
+
+    def calculate_drop(self, drop_deltas) -> int:
+        return int(min(drop_deltas)) - 1
 
     # -- move (game/tetris.py:354-422) ----------------------------------------------------------------
     def move(self, rotations: int, location: int) -> None:
@@ -162,4 +244,6 @@ class Tetris:
                 if not flags[r, c] & (8 | 16)}
 
     def terminate(self):
-        self._env.close()
+        if self._env_handle is not None:
+            self._env_handle.close()
+            self._env_handle = None

@@ -35,6 +35,20 @@ def test_facade_replays_reference_solutions(tp, carve_pool):
     g.terminate()
 
 
+def test_reference_invertability_test_on_global_random(tp):
+    """game/main.py:49-57 verbatim in spirit: seed Python's global random, build the env with the reference's ctor
+    arguments (no config_pool: the native carve generator draws the reference's config), play the recorded solution."""
+    import random
+    for seed, (L, M) in enumerate([(15, 40), (10, 30), (15, 40)]):
+        random.seed(seed)
+        game = tp.Tetris(L, M, warm_reset=False, debug=True)
+        assert len(game.pieces) == M + 1
+        for rotations, location in game.solution:
+            game.move(rotations, location)
+        assert game.state is True
+        game.terminate()
+
+
 def test_facade_matches_oracle_move_by_move(tp, carve_pool):
     rng = np.random.default_rng(0)
     for ep in range(6):
