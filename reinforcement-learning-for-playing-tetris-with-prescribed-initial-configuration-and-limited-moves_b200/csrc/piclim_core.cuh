@@ -38,9 +38,10 @@ enum : uint32_t { S_RUNNING = 0, S_WON = 1, S_LOST = 2 };
 //        bits 16-18 w, bits 20-22 h, bits 24-25 n_rot-1, bit 28 = rot is an alias (rot >= n_rot)
 //   a.y: bo bytes: byte j = rows between the shape's bottom row and the lowest cell of column j
 //        (= h-1-profile[j] with profile the tuple at :25-55); 64 for j >= w so it never wins the max
-//   a.z: (to0, to2) as s16x2, to_j = (height of the highest cell of column j above the bottom row) + 1,
-//        -64 for j >= w so that max(H_j, y + to_j) leaves the column height alone
-//   a.w: (to1, to3) as s16x2   (even/odd pairing: the four new heights then pack into bytes with one multiply-add)
+//   a.z: to bytes: byte j = to_j = (height of the highest cell of column j above the bottom row) + 1, 0 for j >= w;
+//        a covered column's new height is y + to_j (the piece always ends up on top of it), for all four columns at
+//        once y * 0x01010101 + a.z
+//   a.w: cover mask: byte j = 0xFF for j < w (selects the new height), 0 for the columns the shape does not cover
 //   b.x: bo nibbles (4 bits per column, no sentinel) -- used by the column-aligned general path
 //   b.y: (1 << h) - 1      b.z: 20 - h (top-out iff y > 20 - h)      b.w: unused
 // ---------------------------------------------------------------------------------------------
@@ -54,7 +55,7 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
         for (int j = 0; j < 4; ++j) if ((m[i] >> j) & 1) { if (j + 1 > w) w = j + 1; }
     }
     uint32_t cb = 0, bo = 0, bon = 0;
-    uint32_t to[4] = {0xFFC0u, 0xFFC0u, 0xFFC0u, 0xFFC0u};      // -64 as s16
+    uint32_t to4 = 0, cover = 0;
     for (int j = 0; j < 4; ++j) {
         if (j >= w) { bo |= 64u << (8 * j); continue; }
         int lowest = -1, highest = -1;
@@ -64,10 +65,11 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
         }
         bo |= (uint32_t)(h - 1 - lowest) << (8 * j);
         bon |= (uint32_t)(h - 1 - lowest) << (4 * j);
-        to[j] = (uint32_t)(h - highest);
+        to4 |= (uint32_t)(h - highest) << (8 * j);
+        cover |= 0xFFu << (8 * j);
     }
     return OrientEntry{cb | ((uint32_t)w << 16) | ((uint32_t)h << 20) | ((uint32_t)(nrot - 1) << 24) | (alias ? 1u << 28 : 0u),
-                       bo, to[0] | (to[2] << 16), to[1] | (to[3] << 16),
+                       bo, to4, cover,
                        bon, (1u << h) - 1u, (uint32_t)(20 - h), 0u};
 }
 

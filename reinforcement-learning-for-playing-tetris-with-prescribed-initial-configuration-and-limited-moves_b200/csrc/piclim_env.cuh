@@ -70,8 +70,8 @@ __device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t 
 //
 // Fast path (no row clears), per slot, all on packed bytes / halfwords:
 //   y      = max_j(H[c+j] - bo_j)                          hard drop in height form (:424-433)
-//   full   = A[c] & ((col[c+j] | cb_j << y) for j<4) & (hm << y)   rows of the piece that become full (:382-386)
-//   N      = max(H[c+j], y + to_j)  (s16x2 add-max, -64 sentinel keeps columns the piece does not cover)
+//   full   = A[c] & ((col[c+j] + cb_j << y) for j<4) & (hm << y)   rows of the piece that become full (:382-386)
+//   N      = y + to_j on the columns the shape covers, H[c+j] elsewhere (one byte-wise IMAD + one LOP3 select)
 //   agg'   = agg + sum_j (N_j - H_j)                        one VABSDIFF4.U8.ACC
 //   bump'  = bump - old pairs + new pairs                   one VABSDIFF4.U8.ACC + one VABSDIFF
 //   holes' = agg' - (cells + 4)
@@ -98,12 +98,12 @@ __device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, ui
 }
 
 template <int C, class Sink>
-__device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS], const uint32_t (&H16)[12],
+__device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS],
                                           const uint32_t (&col)[14],
                                           const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
-                                          uint32_t flN, uint32_t flT, bool canon, int w,
-                                          int bo0, int bo1, int bo2, int bo3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
-                                          uint32_t TO01, uint32_t TO23, uint32_t hm, int thr,
+                                          uint32_t flN, uint32_t flT, int w,
+                                          int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
+                                          uint32_t TO4, uint32_t cover, uint32_t hm, int thr,
                                           uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
     if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
@@ -111,32 +111,46 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
         if (pend) nsmask |= 1u << C;
         return;
     }
-    const int y = max(max(H[C] - bo0, H[C + 1] - bo1), max(H[C + 2] - bo2, H[C + 3] - bo3));
+    // hard drop in height form.  nb_j = -bo_j is negated once per rotation: nvcc 12.9 / ptxas drops the operand negation when
+    // it folds `H - bo` terms with a constant-zero H (the padding columns) into the 3-input VIMNMX3 (found by the GPU parity
+    // tests: +64 instead of -64 won the max), so no negation is left for it to fold.
+    const int y = max(max(H[C] + nb0, H[C + 1] + nb1), __viaddmax_s32(H[C + 3], nb3, H[C + 2] + nb2));
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
-    const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & (col[C] | mul_fma_pipe(cb0, pw)) & (col[C + 1] | mul_fma_pipe(cb1, pw)) &
-                          (col[C + 2] | mul_fma_pipe(cb2, pw)) & (col[C + 3] | mul_fma_pipe(cb3, pw));
-    const uint32_t Y2 = (uint32_t)y * 0x10001u;
-    const uint32_t N02 = __viaddmax_s16x2(Y2, TO01, H16[C]);          // H16[c] = (H[c], H[c+2]) as s16x2; TO01 = (to0, to2)
-    const uint32_t N13 = __viaddmax_s16x2(Y2, TO23, H16[C + 1]);      // TO23 = (to1, to3)
-    const uint32_t N4 = mad_fma_pipe(N13, 256u, N02);                 // bytes (n0, n1, n2, n3)
+    // the piece lands on empty cells, so `column | piece image` is `column + piece image`: one IMAD per window column
+    const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & mad_fma_pipe(cb0, pw, col[C]) & mad_fma_pipe(cb1, pw, col[C + 1]) &
+                          mad_fma_pipe(cb2, pw, col[C + 2]) & mad_fma_pipe(cb3, pw, col[C + 3]);
+    // new heights of the window as bytes: y + to_j where the shape covers the column, the old height elsewhere
+    const uint32_t N4 = (mad_fma_pipe((uint32_t)y, 0x01010101u, TO4) & cover) | (Hw[C] & ~cover);
     const uint32_t agg2 = __vsadu4(N4, Hw[C]) + agg;
     const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
     uint32_t wnew = agg2 * 0x01000100u + K;
     wnew = b2 * 0x10000u + wnew;
-    const bool pnew = !top && full != 0u;
     if constexpr (Sink::PACKED) {
         // compact form: the flags ride in byte 0 (K and U already carry flN << 3 / flT << 3 for this rotation)
-        wnew = top ? U : wnew;
-        if (C <= 6) { word = wnew; pend = pnew; }
-        else {
-            const bool fits = C + w <= COLS;
-            word = fits ? wnew : (word | (F_ALIAS << 3));
-            pend = fits ? pnew : pend;
+        if (C <= 5) {
+            // Columns every width fits and no later column aliases: no select at all.  The no-clear word is stored unless
+            // a row completes, then U overwrites it when the piece tops out (same thread, same address: ordered).  A slot
+            // that is both (a row of an overflowing piece completes -- very rare) is deferred too; resolve_slot handles it.
+            const bool pnew = full != 0u;
+            if (!pnew) sink.put_packed_col(C, wnew);
+            if (top) sink.put_packed_col(C, U);
+            if (pnew) { pmask |= 1u << C; nsmask |= 1u << C; }
+            pend = pnew && !top;
+        } else {
+            const bool pnew = !top && full != 0u;
+            wnew = top ? U : wnew;
+            if (C == 6) { word = wnew; pend = pnew; }
+            else {
+                const bool fits = C + w <= COLS;
+                word = fits ? wnew : (word | (F_ALIAS << 3));
+                pend = fits ? pnew : pend;
+            }
+            if (pend && (C == 6 || C + w <= COLS)) pmask |= 1u << C;
+            if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
         }
-        if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
-        if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
     } else {
+        const bool pnew = !top && full != 0u;
         wnew = top ? U : wnew;
         const uint32_t fnew = top ? flT : flN;
         if (C <= 6) {                                  // every width fits (w <= 4)
@@ -147,7 +161,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             fl = fits ? fnew : (fl | F_ALIAS);
             pend = fits ? pnew : pend;
         }
-        if (pend && canon && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
+        if (pend && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
         if (!pend) sink.put(r * 10 + C, word, fl); else nsmask |= 1u << C;
     }
 }
@@ -166,9 +180,11 @@ __device__ __forceinline__ void resolve_slot(const uint32_t (&cols)[COLS], const
 #pragma unroll
     for (int k = 0; k < COLS; ++k) x[k] = cols[k];
     const MoveOut m = place_general(x, scr, ss, o, ob, c);
-    const uint32_t f3 = board_features(x, (int)cx.cells + 4 - 10 * m.k);
+    // (a deferred slot may turn out to be a top-out: board unchanged, :372-374)
+    const uint32_t f3 = board_features(x, m.topout ? (int)cx.cells : (int)cx.cells + 4 - 10 * m.k);
     const uint32_t word = (uint32_t)m.k | (f3 << 8);
-    const uint32_t fl = m.k == 0 ? cx.fl_noclear : (((int)cx.lines + m.k >= L) ? F_WIN : cx.fl_noclear);   // :389-391, :415-422
+    const uint32_t fl = m.topout ? F_TOPOUT :
+                        m.k == 0 ? cx.fl_noclear : (((int)cx.lines + m.k >= L) ? F_WIN : cx.fl_noclear);   // :389-391, :415-422
     const int nrot = orient_nrot(o), w = orient_w(o);
     const int cend = (c == COLS - w) ? COLS - 1 : c;
     for (int r2 = r; r2 < 4; r2 += nrot)
@@ -214,9 +230,6 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     Hw[1] = __byte_perm(HB0, HB1, 0x4321); Hw[2] = __byte_perm(HB0, HB1, 0x5432); Hw[3] = __byte_perm(HB0, HB1, 0x6543);
     Hw[5] = __byte_perm(HB1, HB2, 0x4321); Hw[6] = __byte_perm(HB1, HB2, 0x5432); Hw[7] = __byte_perm(HB1, HB2, 0x6543);
     Hw[9] = HB2 >> 8;
-    uint32_t H16[12];                                // H16[c] = (H[c], H[c+2]) as s16x2, zero beyond column 9
-#pragma unroll
-    for (int c = 0; c < 12; ++c) H16[c] = (uint32_t)H[c] | ((uint32_t)H[c + 2] << 16);
     const uint32_t agg = __vsadu4(HB0, 0u) + __vsadu4(HB1, 0u) + __vsadu4(HB2, 0u);
     const uint32_t bump = __vsadu4(Hw[0], Hw[1]) + __vsadu4(Hw[4], Hw[5]) + (uint32_t)__sad(H[8], H[9], 0u);
     uint32_t Bb[COLS];                               // bump minus the pairs a placement at c can change
@@ -245,19 +258,19 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const int w = orient_w(o);
         int cmax_warp = 9;
         if constexpr (UNIFORM) cmax_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(COLS - w));
-        const int bo0 = o.y & 0xFF, bo1 = (o.y >> 8) & 0xFF, bo2 = (o.y >> 16) & 0xFF, bo3 = o.y >> 24;
+        const int nb0 = -(int)(o.y & 0xFF), nb1 = -(int)((o.y >> 8) & 0xFF), nb2 = -(int)((o.y >> 16) & 0xFF), nb3 = -(int)(o.y >> 24);
         const uint32_t cb0 = o.x & 15u, cb1 = (o.x >> 4) & 15u, cb2 = (o.x >> 8) & 15u, cb3 = (o.x >> 12) & 15u;
         const uint32_t afl = orient_alias(o) ? F_ALIAS : 0u;
-        const bool canon = afl == 0u;
+        const bool canon = afl == 0u;               // deferred slots are resolved once, from the canonical rotation
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
         const uint32_t Kr = Sink::PACKED ? K + (flN << 3) : K, Ur = Sink::PACKED ? (U | (flT << 3)) : U;
         uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
         if constexpr (Sink::PACKED) sink.begin_rotation(r);
-#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, H16, col, A, Bb, agg, Kr, Ur, flN, flT, canon, w, bo0, bo1, bo2, bo3, cb0, cb1, cb2, cb3, \
+#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
                                  o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, nsmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
-        pending |= (unsigned long long)pmask << (10 * r);
+        if (canon) pending |= (unsigned long long)pmask << (10 * r);
         if constexpr (UNIFORM) notstored |= (unsigned long long)nsmask << (10 * r);
     }
 

@@ -195,6 +195,40 @@ struct GlobalSink {
     }
 };
 
+// ---- staged output (compact form): the tile's 40 x 128 packed words are collected in shared memory at
+// [slot][thread] -- a store is one STS with an immediate offset, no per-slot 64-bit address arithmetic on the ALU pipe
+// that bounds the kernel -- and leave the SM as 40 contiguous 512-byte rows through the TMA bulk-copy engine
+// (cp.async.bulk shared -> global).  Needs 16-byte aligned rows: n % 4 == 0 and a 16-byte aligned output array;
+// the GlobalSink path serves everything else.
+struct StagedSink {
+    static constexpr bool PACKED = true;
+    uint32_t *out;                                    // s_tile + owner thread
+    uint32_t *orot;
+    __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * THREADS; }
+    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { orot[c * THREADS] = packed; }
+    __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { out[slot * THREADS] = packed; }
+    __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * THREADS] = word | (fl << 3); }
+};
+
+__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+// the rows issued by this thread have been read out of shared memory (the tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// all threads: make the tile written with ordinary stores visible to the bulk-copy engine, then 40 threads ship one row each
+__device__ __forceinline__ void ship_tile(const uint32_t *s_tile, uint32_t *words, int64_t base, int n) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 40) {
+        const int64_t left = (int64_t)n - base;
+        const uint32_t cnt = left < THREADS ? (uint32_t)left : (uint32_t)THREADS;
+        bulk_store_row(words + (size_t)threadIdx.x * (size_t)n + (size_t)base, s_tile + threadIdx.x * THREADS, cnt * 4u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
 // ---- CTA-pooled resolution of the deferred (row-completing) slots -----------------------------------------------
 // Only ~2 lanes of a warp have such a slot in any given iteration, so resolving them in place runs the ~240-instruction
 // general move at 7 % lane utilisation (20 % of the kernel's issue slots on carve-generated boards).  Instead every
@@ -223,9 +257,9 @@ __device__ __forceinline__ void coop_publish(CoopSmem &cs, const Env &e, const P
     }
 }
 
-template <int MODE>
+template <int MODE, bool STAGED = false>
 __device__ __forceinline__ void coop_resolve(CoopSmem &cs, const uint4 *s_tab, uint32_t *scr, int64_t tile_base, uint32_t n,
-                                             uint32_t *words, uint8_t *flags, float4 *ff, int L) {
+                                             uint32_t *words, uint8_t *flags, float4 *ff, int L, uint32_t *s_tile = nullptr) {
     const int total = cs.n_items;
     for (int k = threadIdx.x; k < total; k += THREADS) {
         const int item = cs.items[k], owner = item & 0xFF, slot = item >> 8;
@@ -234,38 +268,55 @@ __device__ __forceinline__ void coop_resolve(CoopSmem &cs, const uint4 *s_tab, u
         for (int j = 0; j < COLS; ++j) cols[j] = cs.env[j * THREADS + owner];
         const uint32_t m0 = cs.env[10 * THREADS + owner];
         const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, cs.env[11 * THREADS + owner], m0 >> 16};
-        const int64_t i = tile_base + owner;
-        GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, nullptr};
-        resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
+        if constexpr (STAGED) {
+            StagedSink sink{s_tile + owner, nullptr};
+            resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
+        } else {
+            const int64_t i = tile_base + owner;
+            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, nullptr};
+            resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
+        }
     }
 }
 
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
 #endif
-template <int MODE>
+template <int MODE, bool STAGED = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
+    static_assert(!STAGED || MODE == 0, "the staged tile holds the compact form");
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ CoopSmem cs;
+    __shared__ __align__(128) uint32_t s_tile[STAGED ? 40 * THREADS : 4];
     TPL_SCRATCH;
     load_table(s_tab);
     const int ntiles = (n + THREADS - 1) / THREADS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
         const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a, d = a;
+        if (i < n) { a = st[i]; b = st[stride + i]; c = st[2 * stride + i]; d = st[3 * stride + i]; }   // in flight across the barrier
+        if (STAGED && threadIdx.x < 40) bulk_wait_read();                        // the previous tile has left shared memory
         if (threadIdx.x == 0) cs.n_items = 0;
         __syncthreads();
         if (i < n) {
-            Env e; load_env(st, stride, i, e);
-            GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
+            Env e; unpack_env(a, b, c, d, e);
             PendingCtx cx;
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            if constexpr (STAGED) {
+                StagedSink sink{s_tile + threadIdx.x, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            } else {
+                GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            }
             coop_publish<MODE>(cs, e, cx);
         }
         __syncthreads();
-        coop_resolve<MODE>(cs, s_tab, scr, base, (uint32_t)n, words, flags, ff, L);
+        coop_resolve<MODE, STAGED>(cs, s_tab, scr, base, (uint32_t)n, words, flags, ff, L, s_tile);
+        if constexpr (STAGED) ship_tile(s_tile, words, base, n);
     }
+    if (STAGED && threadIdx.x < 40) bulk_wait_read();
 }
 
 // Small batches (BASELINE configs[1]: 4096 envs = 32 CTAs on 148 SMs) are latency-bound: one warp per scheduler runs a
@@ -314,11 +365,6 @@ struct TileSink {                                          // packed words at th
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * TILE] = word | (fl << 3); }
     __device__ __forceinline__ void copy(int dst, int src, uint32_t extra) { out[dst * TILE] = out[src * TILE] | (extra << 3); }
 };
-
-__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, uint32_t bytes) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
-}
 
 // sort key of an env from its chunks 2 and 3: pieces with the same rotation count adjacent (O | I S Z | L J T), no piece last
 __device__ __forceinline__ uint32_t sort_key(const uint4 &c, const uint4 &d) {
@@ -424,27 +470,34 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
 // One launch reads each 64-byte record once and writes it once; the memory time of the move hides under the
 // integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
 // =================================================================================================
-template <int MODE>
+template <int MODE, bool STAGED = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
                     const uint4 *__restrict__ pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
                     uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M) {
+    static_assert(!STAGED || MODE == 0, "the staged tile holds the compact form");
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ CoopSmem cs;
+    __shared__ __align__(128) uint32_t s_tile[STAGED ? 40 * THREADS : 4];
     TPL_SCRATCH;
     load_table(s_tab);
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int ntiles = (n + THREADS - 1) / THREADS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
         const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra, rc = ra, rd = ra; uint32_t arot = 0, aloc = 0;
+        if (i < n) {                                                            // in flight across the barrier
+            ra = st[i]; rb = st[stride + i]; rc = st[2 * stride + i]; rd = st[3 * stride + i]; arot = rot[i]; aloc = loc[i];
+        }
+        if (STAGED && threadIdx.x < 40) bulk_wait_read();                        // the previous tile has left shared memory
         if (threadIdx.x == 0) cs.n_items = 0;
         __syncthreads();
         if (i < n) {
-            Env e; load_env(st, stride, i, e);
+            Env e; unpack_env(ra, rb, rc, rd, e);
             const uint32_t was = e.state;
             int k; bool changed;
-            const uint32_t fl = step_env(e, s_tab, scr, THREADS, rot[i], loc[i], L, M, k, changed);
+            const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
             if (dlines) dlines[i] = (int8_t)k;
             if (flags) flags[i] = (uint8_t)fl;
             if (sto) sto[i] = (int8_t)e.state;
@@ -466,14 +519,21 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
                 st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
             }
             st[3 * stride + i] = pack_meta(e);
-            GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, nullptr};
             PendingCtx cx;
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            if constexpr (STAGED) {
+                StagedSink sink{s_tile + threadIdx.x, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            } else {
+                GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            }
             coop_publish<MODE>(cs, e, cx);
         }
         __syncthreads();
-        coop_resolve<MODE>(cs, s_tab, scr, base, (uint32_t)n, words, aflags, ff, L);
+        coop_resolve<MODE, STAGED>(cs, s_tab, scr, base, (uint32_t)n, words, aflags, ff, L, s_tile);
+        if constexpr (STAGED) ship_tile(s_tile, words, base, n);
     }
+    if (STAGED && threadIdx.x < 40) bulk_wait_read();
     if (stats) flush_stats(acc, stats);
 }
 
@@ -545,6 +605,14 @@ static bool sorted_path_ok(int n, const void *feats) {
     static int enabled = -1;
     if (enabled < 0) { const char *v = getenv("TPL_SORTED_AFTERSTATES"); enabled = (v && v[0] == '1') ? 1 : 0; }
     return enabled && n >= 2 * TILE && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
+}
+
+// The compact output form leaves the SM through shared memory + TMA bulk stores when its rows are 16-byte granular
+// (TPL_NO_STAGED_OUTPUT=1 forces the direct-store kernels: used by the tests to cover both paths).
+static bool staged_ok(int n, const void *feats) {
+    static int disabled = -1;
+    if (disabled < 0) { const char *v = getenv("TPL_NO_STAGED_OUTPUT"); disabled = (v && v[0] == '1') ? 1 : 0; }
+    return !disabled && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
 }
 
 static unsigned grid_persistent(int n, int blocks_per_sm) {
@@ -641,7 +709,8 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
         else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
         return check_launch("tpl_afterstates(split)");
     }
-    if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    if (feats && !flags && staged_ok(n, feats)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
     else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
@@ -664,9 +733,10 @@ int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *ro
     uint4 *sp = (uint4 *)state; const uint4 *pp = (const uint4 *)pool; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
     unsigned long long *sq = (unsigned long long *)stats;
     const unsigned g = grid_persistent(n, 8);
-#define TPL_SO(MODE) step_observe_kernel<MODE><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
+#define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
                                                                     seed, env_base, gen_count, w, aflags, f, L, M)
-    if (feats && !aflags) TPL_SO(0);
+    if (feats && !aflags && staged_ok(n, feats)) TPL_SO(0, true);
+    else if (feats && !aflags) TPL_SO(0);
     else if (feats && !feats_f32) TPL_SO(1);
     else if (!feats) TPL_SO(2);
     else TPL_SO(3);

@@ -51,6 +51,7 @@ static inline uint32_t __viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     }
     return r;
 }
+static inline int __viaddmax_s32(int a, int b, int c) { return a + b > c ? a + b : c; }
 static inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) { return v; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
