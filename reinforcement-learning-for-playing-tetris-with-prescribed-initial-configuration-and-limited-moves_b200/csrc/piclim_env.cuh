@@ -109,6 +109,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
         else { fl |= F_ALIAS; if (!pend) sink.put(r * 10 + C, word, fl); }
         if (pend) nsmask |= 1u << C;
+        if constexpr (Sink::PACKED) sink.next_col();
         return;
     }
     // hard drop in height form.  nb_j = -bo_j is negated once per rotation: nvcc 12.9 / ptxas drops the operand negation when
@@ -149,6 +150,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             if (pend && (C == 6 || C + w <= COLS)) pmask |= 1u << C;
             if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
         }
+        sink.next_col();
     } else {
         const bool pnew = !top && full != 0u;
         wnew = top ? U : wnew;

@@ -176,12 +176,20 @@ struct GlobalSink {
     static constexpr bool PACKED = (MODE == 0);
     uint32_t *words; uint8_t *flags; float4 *ff;      // already offset by the env index
     uint32_t n;
-    uint32_t *wrot;                                   // row of the current rotation's column 0
-    __device__ __forceinline__ void begin_rotation(int r) { wrot = words + (size_t)((uint32_t)(r * 10) * n); }
-    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) {
-        uint64_t addr;                                // wrot + c * n words, as ONE IMAD.WIDE on the FMA pipe (not an ALU LEA pair)
-        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"((uint32_t)c * n), "l"(wrot));
-        *reinterpret_cast<uint32_t *>(addr) = packed;
+    uint32_t one;                                     // the value 1 from a kernel parameter, i.e. opaque to ptxas (see next_col)
+    uint32_t *pcol;                                   // compact form: this env's word of the current (rotation, column)
+    __device__ __forceinline__ void begin_rotation(int r) {
+#ifdef __CUDA_ARCH__
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(pcol) : "r"((uint32_t)(r * 10) * 4u), "r"(n), "l"(words));
+#endif
+    }
+    __device__ __forceinline__ void put_packed_col(int, uint32_t packed) { *pcol = packed; }
+    // pcol += n words as ONE 64-bit multiply-add on the FMA pipe: with an immediate multiplier ptxas strength-reduces
+    // it to a LEA / LEA.HI.X pair on the ALU pipe, which is the pipe that bounds the kernel.
+    __device__ __forceinline__ void next_col() {
+#ifdef __CUDA_ARCH__
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(pcol) : "r"(n * 4u), "r"(one));
+#endif
     }
     __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { words[(uint32_t)slot * n] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
@@ -195,128 +203,124 @@ struct GlobalSink {
     }
 };
 
-// ---- staged output (compact form): the tile's 40 x 128 packed words are collected in shared memory at
-// [slot][thread] -- a store is one STS with an immediate offset, no per-slot 64-bit address arithmetic on the ALU pipe
-// that bounds the kernel -- and leave the SM as 40 contiguous 512-byte rows through the TMA bulk-copy engine
-// (cp.async.bulk shared -> global).  Needs 16-byte aligned rows: n % 4 == 0 and a 16-byte aligned output array;
-// the GlobalSink path serves everything else.
-struct StagedSink {
-    static constexpr bool PACKED = true;
-    uint32_t *out;                                    // s_tile + owner thread
-    uint32_t *orot;
-    __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * THREADS; }
-    __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { orot[c * THREADS] = packed; }
-    __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { out[slot * THREADS] = packed; }
-    __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * THREADS] = word | (fl << 3); }
+// ---- warp-private queues of deferred (row-completing) slots ---------------------------------------------------------
+// Only ~2 lanes of a warp have such a slot in any given tile, so resolving them in place runs the ~300-instruction general
+// move at a few % lane utilisation, and pooling them per CTA (the previous design) costs two block-wide barriers per tile:
+// ncu attributed 27 % of all warp samples to barrier stalls, because the short resolve phase keeps one warp busy while
+// three wait.  Here every warp owns a small FIFO in shared memory: lanes append their deferred slots (and park the ten
+// columns of their env once), the warp keeps walking through its tiles, and whenever 32 slots have accumulated they are
+// resolved by a full warp.  No __syncthreads in the tile loop at all: the 16 resident warps of an SM drift freely and
+// cover each other's load latency.
+constexpr int WQ_ENVS = 64;          // env entries: < 32 live after a resolve + <= 32 new per tile
+constexpr int WQ_ITEMS = 512;        // deferred slots; a lane whose slots do not fit resolves them itself (never seen in practice)
+struct WarpQueue {
+    uint32_t env[13 * WQ_ENVS];      // [k][entry]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines, env index
+    uint16_t items[WQ_ITEMS];        // entry | slot << 6
 };
-
-__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, uint32_t bytes) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
-}
-// the rows issued by this thread have been read out of shared memory (the tile may be overwritten)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// all threads: make the tile written with ordinary stores visible to the bulk-copy engine, then 40 threads ship one row each
-__device__ __forceinline__ void ship_tile(const uint32_t *s_tile, uint32_t *words, int64_t base, int n) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x < 40) {
-        const int64_t left = (int64_t)n - base;
-        const uint32_t cnt = left < THREADS ? (uint32_t)left : (uint32_t)THREADS;
-        bulk_store_row(words + (size_t)threadIdx.x * (size_t)n + (size_t)base, s_tile + threadIdx.x * THREADS, cnt * 4u);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-}
-
-// ---- CTA-pooled resolution of the deferred (row-completing) slots -----------------------------------------------
-// Only ~2 lanes of a warp have such a slot in any given iteration, so resolving them in place runs the ~240-instruction
-// general move at 7 % lane utilisation (20 % of the kernel's issue slots on carve-generated boards).  Instead every
-// thread appends its deferred slots to a shared list, parks its ten columns in shared memory, and after one barrier
-// the list is worked off by consecutive threads: full warps, and most warps skip the phase altogether.
-struct CoopSmem {
-    uint32_t env[12 * THREADS];       // [k][tid]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines
-    uint16_t items[40 * THREADS];     // owner tid | slot << 8
-    int n_items;
-};
+struct WqPos { uint32_t head, tail, ehead, etail; };      // warp-uniform, monotonically increasing (indices are taken modulo)
 
 template <int MODE>
-__device__ __forceinline__ void coop_publish(CoopSmem &cs, const Env &e, const PendingCtx &cx) {
-    if (!cx.mask) return;
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, const uint4 *s_tab, uint32_t *scr, uint32_t n,
+                                           uint32_t *words, uint8_t *flags, float4 *ff, int L, uint32_t one) {
+    const uint32_t lane = threadIdx.x & 31u;
+    while (p.tail - p.head >= 32u || (flush && p.tail != p.head)) {
+        const uint32_t live = p.tail - p.head, take = live < 32u ? live : 32u;
+        if (lane < take) {
+            const uint32_t item = q.items[(p.head + lane) % WQ_ITEMS], entry = item & 63u, slot = item >> 6;
+            uint32_t cols[COLS];
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) cs.env[k * THREADS + tid] = e.col[k];
-    cs.env[10 * THREADS + tid] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
-    cs.env[11 * THREADS + tid] = cx.lines;
-    unsigned long long m = cx.mask;
-    int at = atomicAdd(&cs.n_items, __popcll(m));
-    while (m) {
-        const int s = __ffsll((long long)m) - 1;
-        m &= m - 1ull;
-        cs.items[at++] = (uint16_t)(tid | (s << 8));
+            for (int j = 0; j < COLS; ++j) cols[j] = q.env[j * WQ_ENVS + entry];
+            const uint32_t m0 = q.env[10 * WQ_ENVS + entry];
+            const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, q.env[11 * WQ_ENVS + entry], m0 >> 16};
+            const uint32_t i = q.env[12 * WQ_ENVS + entry];
+            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, one, nullptr};
+            resolve_slot(cols, cx, (int)slot, s_tab, scr, THREADS, L, sink);
+        }
+        __syncwarp();
+        p.head += take;
+        if (p.head != p.tail) p.ehead += ((q.items[p.head % WQ_ITEMS] & 63u) - p.ehead) & 63u;      // entry of the first slot left
+        else p.ehead = p.etail;
     }
 }
 
-template <int MODE, bool STAGED = false>
-__device__ __forceinline__ void coop_resolve(CoopSmem &cs, const uint4 *s_tab, uint32_t *scr, int64_t tile_base, uint32_t n,
-                                             uint32_t *words, uint8_t *flags, float4 *ff, int L, uint32_t *s_tile = nullptr) {
-    const int total = cs.n_items;
-    for (int k = threadIdx.x; k < total; k += THREADS) {
-        const int item = cs.items[k], owner = item & 0xFF, slot = item >> 8;
-        uint32_t cols[COLS];
+// every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer)
+template <int MODE>
+__device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e, const PendingCtx &cx, uint32_t i,
+                                           const uint4 *s_tab, uint32_t *scr, uint32_t n, uint32_t *words, uint8_t *flags,
+                                           float4 *ff, int L, uint32_t one) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t cnt = (uint32_t)__popcll(cx.mask);
+    const unsigned have = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
+    if (have == 0u) return;
+    uint32_t incl = cnt;
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) cols[j] = cs.env[j * THREADS + owner];
-        const uint32_t m0 = cs.env[10 * THREADS + owner];
-        const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, cs.env[11 * THREADS + owner], m0 >> 16};
-        if constexpr (STAGED) {
-            StagedSink sink{s_tile + owner, nullptr};
-            resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
-        } else {
-            const int64_t i = tile_base + owner;
-            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, nullptr};
-            resolve_slot(cols, cx, slot, s_tab, scr, THREADS, L, sink);
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    const uint32_t room = WQ_ITEMS - (p.tail - p.head);
+    const bool fits = incl <= room;                                    // monotone in the lane index
+    const unsigned fit = __ballot_sync(0xFFFFFFFFu, cnt != 0u && fits);
+    if (cnt != 0u) {
+        if (fits) {
+            const uint32_t entry = (p.etail + (uint32_t)__popc(fit & ((1u << lane) - 1u))) % WQ_ENVS;
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) q.env[k * WQ_ENVS + entry] = e.col[k];
+            q.env[10 * WQ_ENVS + entry] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
+            q.env[11 * WQ_ENVS + entry] = cx.lines;
+            q.env[12 * WQ_ENVS + entry] = i;
+            unsigned long long m = cx.mask;
+            uint32_t at = p.tail + incl - cnt;
+            while (m) {
+                const int sl = __ffsll((long long)m) - 1;
+                m &= m - 1ull;
+                q.items[at++ % WQ_ITEMS] = (uint16_t)(entry | ((uint32_t)sl << 6));
+            }
+        } else {                                                       // queue full: this lane resolves its own slots now
+            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, one, nullptr};
+            unsigned long long m = cx.mask;
+            while (m) {
+                const int sl = __ffsll((long long)m) - 1;
+                m &= m - 1ull;
+                resolve_slot(e.col, cx, sl, s_tab, scr, THREADS, L, sink);
+            }
         }
     }
+    if (fit) {
+        p.tail += __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(fit));      // inclusive count at the last lane that fits
+        p.etail += (uint32_t)__popc(fit);
+    }
+    __syncwarp();
+    wq_resolve<MODE>(q, p, false, s_tab, scr, n, words, flags, ff, L, one);
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr)); }
 
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
 #endif
-template <int MODE, bool STAGED = false>
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
-                   uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
-    static_assert(!STAGED || MODE == 0, "the staged tile holds the compact form");
+                   uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
     __shared__ uint4 s_tab[TAB_WORDS4];
-    __shared__ CoopSmem cs;
-    __shared__ __align__(128) uint32_t s_tile[STAGED ? 40 * THREADS : 4];
+    __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
-    const int ntiles = (n + THREADS - 1) / THREADS;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
-        const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a, d = a;
-        if (i < n) { a = st[i]; b = st[stride + i]; c = st[2 * stride + i]; d = st[3 * stride + i]; }   // in flight across the barrier
-        if (STAGED && threadIdx.x < 40) bulk_wait_read();                        // the previous tile has left shared memory
-        if (threadIdx.x == 0) cs.n_items = 0;
-        __syncthreads();
+    WarpQueue &q = s_wq[threadIdx.x >> 5];
+    WqPos qp{0u, 0u, 0u, 0u};
+    const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
+    for (int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5); t < wtiles; t += wstep) {   // warp-uniform trip count
+        const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
+        PendingCtx cx; cx.mask = 0ull;
+        Env e;
         if (i < n) {
-            Env e; unpack_env(a, b, c, d, e);
-            PendingCtx cx;
-            if constexpr (STAGED) {
-                StagedSink sink{s_tile + threadIdx.x, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
-            } else {
-                GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
-            }
-            coop_publish<MODE>(cs, e, cx);
+            load_env(st, stride, i, e);
+            const int64_t i2 = i + (int64_t)wstep * 32;
+            if (i2 < n) { prefetch_l2(st + i2); prefetch_l2(st + stride + i2); prefetch_l2(st + 2 * stride + i2); prefetch_l2(st + 3 * stride + i2); }
+            GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
         }
-        __syncthreads();
-        coop_resolve<MODE, STAGED>(cs, s_tab, scr, base, (uint32_t)n, words, flags, ff, L, s_tile);
-        if constexpr (STAGED) ship_tile(s_tile, words, base, n);
+        wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
     }
-    if (STAGED && threadIdx.x < 40) bulk_wait_read();
+    wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
 }
 
 // Small batches (BASELINE configs[1]: 4096 envs = 32 CTAs on 148 SMs) are latency-bound: one warp per scheduler runs a
@@ -325,7 +329,7 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
 template <int MODE>
 __global__ void __launch_bounds__(THREADS)
 afterstates_split_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
-                         uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M) {
+                         uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
     __shared__ uint4 s_tab[TAB_WORDS4];
     TPL_SCRATCH;
     load_table(s_tab);
@@ -334,7 +338,7 @@ afterstates_split_kernel(const uint4 *__restrict__ st, int64_t stride, int n, ui
     const int r = (int)(idx & 3);
     if (i >= n) return;
     Env e; load_env(st, stride, i, e);
-    GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, nullptr};
+    GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
     afterstates_env(e, s_tab, scr, THREADS, L, M, sink, r, r + 1);
 }
 
@@ -361,10 +365,16 @@ struct TileSink {                                          // packed words at th
     uint32_t *orot;
     __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * TILE; }
     __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { orot[c * TILE] = packed; }
+    __device__ __forceinline__ void next_col() {}
     __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { out[slot * TILE] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * TILE] = word | (fl << 3); }
     __device__ __forceinline__ void copy(int dst, int src, uint32_t extra) { out[dst * TILE] = out[src * TILE] | (extra << 3); }
 };
+
+__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
 
 // sort key of an env from its chunks 2 and 3: pieces with the same rotation count adjacent (O | I S Z | L J T), no piece last
 __device__ __forceinline__ uint32_t sort_key(const uint4 &c, const uint4 &d) {
@@ -470,31 +480,29 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
 // One launch reads each 64-byte record once and writes it once; the memory time of the move hides under the
 // integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
 // =================================================================================================
-template <int MODE, bool STAGED = false>
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
                     const uint4 *__restrict__ pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
-                    uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M) {
-    static_assert(!STAGED || MODE == 0, "the staged tile holds the compact form");
+                    uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
     __shared__ uint4 s_tab[TAB_WORDS4];
-    __shared__ CoopSmem cs;
-    __shared__ __align__(128) uint32_t s_tile[STAGED ? 40 * THREADS : 4];
+    __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
+    WarpQueue &q = s_wq[threadIdx.x >> 5];
+    WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int ntiles = (n + THREADS - 1) / THREADS;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // CTA-uniform trip count (barriers inside)
-        const int64_t base = (int64_t)tile * THREADS, i = base + threadIdx.x;
-        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra, rc = ra, rd = ra; uint32_t arot = 0, aloc = 0;
-        if (i < n) {                                                            // in flight across the barrier
-            ra = st[i]; rb = st[stride + i]; rc = st[2 * stride + i]; rd = st[3 * stride + i]; arot = rot[i]; aloc = loc[i];
-        }
-        if (STAGED && threadIdx.x < 40) bulk_wait_read();                        // the previous tile has left shared memory
-        if (threadIdx.x == 0) cs.n_items = 0;
-        __syncthreads();
+    const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
+    for (int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5); t < wtiles; t += wstep) {   // warp-uniform trip count
+        const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
+        PendingCtx cx; cx.mask = 0ull;
+        Env e;
         if (i < n) {
-            Env e; unpack_env(ra, rb, rc, rd, e);
+            load_env(st, stride, i, e);
+            const uint32_t arot = rot[i], aloc = loc[i];
+            const int64_t i2 = i + (int64_t)wstep * 32;
+            if (i2 < n) { prefetch_l2(st + i2); prefetch_l2(st + stride + i2); prefetch_l2(st + 2 * stride + i2); prefetch_l2(st + 3 * stride + i2); }
             const uint32_t was = e.state;
             int k; bool changed;
             const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
@@ -519,21 +527,12 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
                 st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
             }
             st[3 * stride + i] = pack_meta(e);
-            PendingCtx cx;
-            if constexpr (STAGED) {
-                StagedSink sink{s_tile + threadIdx.x, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
-            } else {
-                GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
-            }
-            coop_publish<MODE>(cs, e, cx);
+            GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
         }
-        __syncthreads();
-        coop_resolve<MODE, STAGED>(cs, s_tab, scr, base, (uint32_t)n, words, aflags, ff, L, s_tile);
-        if constexpr (STAGED) ship_tile(s_tile, words, base, n);
+        wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
     }
-    if (STAGED && threadIdx.x < 40) bulk_wait_read();
+    wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
     if (stats) flush_stats(acc, stats);
 }
 
@@ -605,14 +604,6 @@ static bool sorted_path_ok(int n, const void *feats) {
     static int enabled = -1;
     if (enabled < 0) { const char *v = getenv("TPL_SORTED_AFTERSTATES"); enabled = (v && v[0] == '1') ? 1 : 0; }
     return enabled && n >= 2 * TILE && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
-}
-
-// The compact output form leaves the SM through shared memory + TMA bulk stores when its rows are 16-byte granular
-// (TPL_NO_STAGED_OUTPUT=1 forces the direct-store kernels: used by the tests to cover both paths).
-static bool staged_ok(int n, const void *feats) {
-    static int disabled = -1;
-    if (disabled < 0) { const char *v = getenv("TPL_NO_STAGED_OUTPUT"); disabled = (v && v[0] == '1') ? 1 : 0; }
-    return !disabled && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
 }
 
 static unsigned grid_persistent(int n, int blocks_per_sm) {
@@ -703,17 +694,16 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
     }
     if (grid_for(n) < 2u * (unsigned)sm_count()) {                 // fewer than two CTAs per SM: split envs over 4 threads
         const unsigned g4 = (unsigned)(((int64_t)n * 4 + THREADS - 1) / THREADS);
-        if (feats && !flags) afterstates_split_kernel<0><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-        else if (feats && !feats_f32) afterstates_split_kernel<1><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-        else if (!feats) afterstates_split_kernel<2><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-        else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+        if (feats && !flags) afterstates_split_kernel<0><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+        else if (feats && !feats_f32) afterstates_split_kernel<1><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+        else if (!feats) afterstates_split_kernel<2><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+        else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
         return check_launch("tpl_afterstates(split)");
     }
-    if (feats && !flags && staged_ok(n, feats)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
-    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M);
+    if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
     return check_launch("tpl_afterstates");
 }
 
@@ -734,9 +724,8 @@ int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *ro
     unsigned long long *sq = (unsigned long long *)stats;
     const unsigned g = grid_persistent(n, 8);
 #define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
-                                                                    seed, env_base, gen_count, w, aflags, f, L, M)
-    if (feats && !aflags && staged_ok(n, feats)) TPL_SO(0, true);
-    else if (feats && !aflags) TPL_SO(0);
+                                                                    seed, env_base, gen_count, w, aflags, f, L, M, 1u)
+    if (feats && !aflags) TPL_SO(0);
     else if (feats && !feats_f32) TPL_SO(1);
     else if (!feats) TPL_SO(2);
     else TPL_SO(3);

@@ -1,5 +1,5 @@
-"""Static SASS view of a kernel in the built library: total instruction count and an opcode histogram of its biggest
-backward-branch loop (for the afterstate kernels: the rotation loop, 10 unrolled slots).
+"""Static SASS view of a kernel in the built library: total instruction count and an opcode histogram of the rotation
+loop of the afterstate kernels (the smallest loop holding the 10 unrolled slots).
 
     python scripts/sass_hist.py step_observe_kernelILi0 [--dump]
 """
@@ -31,8 +31,8 @@ for k, (addr, text) in enumerate(ins):
         body = [x for x in ins if t <= x[0] <= addr]
         if "--loops" in sys.argv:
             print(f"  loop {t:#x}..{addr:#x}: {len(body)} instructions")
-        # the rotation loop is the biggest loop without an inner barrier
-        if not any("BAR.SYNC" in x[1] for x in body) and (best is None or len(body) > len(best)):
+        # the rotation loop: the smallest loop that holds the ten unrolled slots (two VABSDIFF4 each)
+        if sum("VABSDIFF4" in x[1] for x in body) >= 10 and (best is None or len(body) < len(best)):
             best = body
 ALU = ("LOP3", "SEL", "VIADDMNMX", "VABSDIFF", "SHF", "VIADD", "VIMNMX", "LEA", "ISETP", "PRMT", "IADD3", "PLOP3", "IABS", "MOV", "P2R", "R2P", "BMSK", "SGXT")
 FMA = ("IMAD", "FFMA", "FMUL", "FADD")
@@ -43,7 +43,7 @@ for _, text in best:
     base = op.split(".")[0]
     h[op] += 1
     pipes["alu" if base in ALU else "fma" if base in FMA else "other"] += 1
-print(f"biggest barrier-free loop: {len(best)} instructions; alu {pipes['alu']} fma {pipes['fma']} other {pipes['other']}")
+print(f"rotation loop: {len(best)} instructions; alu {pipes['alu']} fma {pipes['fma']} other {pipes['other']}")
 for op, c in h.most_common():
     print(f"  {c:4d} {op}")
 if "--dump" in sys.argv:
