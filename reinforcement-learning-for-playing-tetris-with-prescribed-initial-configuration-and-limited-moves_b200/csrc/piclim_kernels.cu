@@ -292,6 +292,28 @@ __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e,
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr)); }
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" :: "l"(ptr)); }
+
+// ---- record pipeline: the four 16-byte chunks of the NEXT tile's records travel global -> shared memory with cp.async
+// (LDGSTS: no registers held while in flight) during the ~2 300 instructions the warp spends on the current tile, so a
+// tile starts with four LDS.128 instead of four exposed DRAM round trips (ncu: long-scoreboard was the top stall reason).
+struct RecordStage { uint4 chunk[4][32]; };            // one per warp
+__device__ __forceinline__ void stage_issue(RecordStage &rs, const uint4 *st, int64_t stride, int64_t i, int n) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int64_t ic = i < n ? i : (int64_t)n - 1;      // out-of-range lanes copy a valid record they never use
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&rs.chunk[j][lane]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(st + j * stride + ic) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_take(RecordStage &rs, Env &e) {
+    const uint32_t lane = threadIdx.x & 31u;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const uint4 a = rs.chunk[0][lane], b = rs.chunk[1][lane], c = rs.chunk[2][lane], d = rs.chunk[3][lane];   // own copies only
+    unpack_env(a, b, c, d, e);
+}
 
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
@@ -304,17 +326,20 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
+    __shared__ RecordStage s_stage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
+    RecordStage &rs = s_stage[threadIdx.x >> 5];
     WqPos qp{0u, 0u, 0u, 0u};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
-    for (int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5); t < wtiles; t += wstep) {   // warp-uniform trip count
+    int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
+    if (t < wtiles) stage_issue(rs, st, stride, (int64_t)t * 32 + (threadIdx.x & 31), n);
+    for (; t < wtiles; t += wstep) {                                                                    // warp-uniform trip count
         const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
         PendingCtx cx; cx.mask = 0ull;
         Env e;
+        stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
+        if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
         if (i < n) {
-            load_env(st, stride, i, e);
-            const int64_t i2 = i + (int64_t)wstep * 32;
-            if (i2 < n) { prefetch_l2(st + i2); prefetch_l2(st + stride + i2); prefetch_l2(st + 2 * stride + i2); prefetch_l2(st + 3 * stride + i2); }
             GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
             afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
         }
@@ -490,19 +515,36 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
+    __shared__ RecordStage s_stage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
+    RecordStage &rs = s_stage[threadIdx.x >> 5];
     WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
-    for (int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5); t < wtiles; t += wstep) {   // warp-uniform trip count
+    int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
+    // the next tile's action and episode number ride in three registers; its records in shared memory (stage_issue)
+    uint32_t nrot = 0, nloc = 0, nep = 0;
+    if (t < wtiles) {
+        const int64_t i0 = (int64_t)t * 32 + (threadIdx.x & 31);
+        stage_issue(rs, st, stride, i0, n);
+        if (i0 < n) { nrot = rot[i0]; nloc = loc[i0]; nep = episode ? episode[i0] : 0u; }
+    }
+    for (; t < wtiles; t += wstep) {                                                                    // warp-uniform trip count
         const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
         PendingCtx cx; cx.mask = 0ull;
         Env e;
-        if (i < n) {
-            load_env(st, stride, i, e);
-            const uint32_t arot = rot[i], aloc = loc[i];
+        stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
+        const uint32_t arot = nrot, aloc = nloc, ep1 = nep + 1u;
+        {
             const int64_t i2 = i + (int64_t)wstep * 32;
-            if (i2 < n) { prefetch_l2(st + i2); prefetch_l2(st + stride + i2); prefetch_l2(st + 2 * stride + i2); prefetch_l2(st + 3 * stride + i2); }
+            if (t + wstep < wtiles) stage_issue(rs, st, stride, i2, n);
+            if (i2 < n) { nrot = rot[i2]; nloc = loc[i2]; nep = episode ? episode[i2] : 0u; }
+        }
+        if (i < n) {
+            // Which pool record a reset would install depends only on (seed, env, episode + 1): draw it now and pull the record
+            // towards L1, so the reset below -- taken by some lane of almost every warp -- does not wait for an L2 gather.
+            uint32_t kcfg = 0;
+            if (pool) { kcfg = config_index(seed, env_base + (uint64_t)i, ep1, K); prefetch_l1(pool + 4 * (size_t)kcfg); }
             const uint32_t was = e.state;
             int k; bool changed;
             const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
@@ -515,9 +557,8 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
                 if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
             }
             if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {            // TPL_RESET_DONE semantics
-                uint32_t ep = episode ? episode[i] + 1u : 1u;
-                if (episode) episode[i] = ep;
-                install_config(e, pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
+                if (episode) episode[i] = ep1;
+                install_config(e, pool, kcfg, seed, env_base + (uint64_t)i, ep1, gen_count);
                 acc[7] += 1;
                 changed = true;
             }
