@@ -720,7 +720,11 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
     if (n == 0) return 0;
     const cudaStream_t s = (cudaStream_t)stream;
     const uint4 *st = (const uint4 *)state; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
-    const unsigned g = grid_persistent(n, 8);
+    static int as_blocks_per_sm = 0;                   // one resident wave, as for the fused kernel
+    if (!as_blocks_per_sm &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&as_blocks_per_sm, afterstates_kernel<0>, THREADS, 0) != cudaSuccess || as_blocks_per_sm <= 0))
+        as_blocks_per_sm = 4;
+    const unsigned g = grid_persistent(n, as_blocks_per_sm);
     if (feats && !flags && !feats_f32 && sorted_path_ok(n, feats)) {
         static bool attr_set = false;
         if (!attr_set) {
@@ -763,7 +767,13 @@ int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *ro
     const cudaStream_t s = (cudaStream_t)stream;
     uint4 *sp = (uint4 *)state; const uint4 *pp = (const uint4 *)pool; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
     unsigned long long *sq = (unsigned long long *)stats;
-    const unsigned g = grid_persistent(n, 8);
+    // exactly one resident wave of persistent CTAs (4 per SM at 128 registers): every warp walks through its share of the
+    // 32-env tiles, and the partly filled last round of its deferred-slot queue is paid once per warp
+    static int so_blocks_per_sm = 0;
+    if (!so_blocks_per_sm &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<0>, THREADS, 0) != cudaSuccess || so_blocks_per_sm <= 0))
+        so_blocks_per_sm = 4;
+    const unsigned g = grid_persistent(n, so_blocks_per_sm);
 #define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
                                                                     seed, env_base, gen_count, w, aflags, f, L, M, 1u)
     if (feats && !aflags) TPL_SO(0);
