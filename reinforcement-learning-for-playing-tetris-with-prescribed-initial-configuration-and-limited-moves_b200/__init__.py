@@ -2,7 +2,8 @@
 behind its own ``Tetris`` interface, on hand-written sm_100a CUDA kernels reached through a C ABI
 (``include/tetris_piclim.h``).  Importing the env classes loads ``csrc/libtetris_piclim_sm100.so``; there is no
 CPU fallback."""
-from .configs import ConfigPool, carve_pool, concat_pools, gen_pieces, load_pool, save_pool, synthetic_pool  # noqa: F401
+from .configs import (ConfigPool, carve_pool, concat_pools, forward_games, forward_pool, gen_pieces, load_pool,  # noqa: F401
+                      save_pool, synthetic_pool)
 from . import build  # noqa: F401
 from ._lib import TplError, launch_count  # noqa: F401
 from .host_env import HostBatchedTetris, PinnedArray  # noqa: F401

@@ -57,10 +57,12 @@ CARVE_LIB_PATH = os.path.join(CSRC, "libpiclim_carve.so")
 
 
 def build_carve(force: bool = False) -> str:
-    """The native prescribed-config generator (host code, g++)."""
-    src = os.path.join(CSRC, "carve_gen.cpp")
-    if force or not os.path.exists(CARVE_LIB_PATH) or os.path.getmtime(CARVE_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", CARVE_LIB_PATH, src])
+    """The native prescribed-config generators (host code, g++): the carving generator of game/tetris.py and the
+    forward generator + solver of game/tetris_algo_main."""
+    srcs = [os.path.join(CSRC, f) for f in ("carve_gen.cpp", "forward_gen.cpp")]
+    deps = srcs + [os.path.join(CSRC, "pyrandom.h")]
+    if force or not os.path.exists(CARVE_LIB_PATH) or any(os.path.getmtime(CARVE_LIB_PATH) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", CARVE_LIB_PATH] + srcs)
     return CARVE_LIB_PATH
 
 

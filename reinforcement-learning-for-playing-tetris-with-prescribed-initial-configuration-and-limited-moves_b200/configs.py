@@ -139,6 +139,8 @@ def _carve():
         lib.carve_generate_from_state.argtypes = [V, ctypes.c_int, ctypes.c_int, V, V, ctypes.c_int, V, V, V]
         lib.carve_apply.restype = ctypes.c_int
         lib.carve_apply.argtypes = [V, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.forward_generate.restype = ctypes.c_int
+        lib.forward_generate.argtypes = [ctypes.c_uint64] + [ctypes.c_int] * 5 + [V] * 6 + [ctypes.c_int]
         _carve_lib = lib
     return _carve_lib
 
@@ -196,6 +198,50 @@ def carve_pool(K: int, L: int, M: int, seed0: int = 0, threads: Optional[int] = 
     if rc != 0:
         raise ValueError("carve_generate rejected its arguments (1 <= L <= 16, M >= 1)")
     return ConfigPool(rows, pieces, npieces, sols, nsol)
+
+
+def forward_games(goal: int, tetrominoes: int, seed0: int = 0, count: int = 100, initial_height_max: int = 4,
+                  max_attempts: int = 1000, threads: Optional[int] = None) -> dict:
+    """The reference's FORWARD producer for seeds seed0 .. seed0+count-1, natively (csrc/forward_gen.cpp):
+    ``TetrisGameGenerator(seed, goal, tetrominoes, initial_height_max)`` (``game/tetris_algo_main/TetrisGameGenerator.py``)
+    followed by ``TetrisSolver(board, sequence, goal, max_attempts).solve()`` (``TetrisSolver.py:112-163``), i.e.
+    ``main.py:generate_game`` / ``solve_game``.  Returns arrays: ``rows`` u16[count, 20], ``letters`` u8[count, tetrominoes]
+    (the sequence as piece ids of ``game/tetris.py``, ``piece_translations`` ``:8-16``), ``solvable``, ``failed`` (the solver's
+    failed_attempts), ``moves`` i8[count, tetrominoes, 3] (the solver's stack: name index in I J L O S T Z, rotation in the
+    generator's own table, column) and ``nmoves``.  ``max_attempts < 0`` generates without solving."""
+    import ctypes
+    import os
+    if not 1 <= tetrominoes <= 255:
+        raise ValueError("1 <= tetrominoes <= 255")
+    rows = np.zeros((count, 20), np.uint16)
+    letters = np.zeros((count, tetrominoes), np.uint8)
+    solvable, nmoves = np.zeros(count, np.uint8), np.zeros(count, np.uint8)
+    failed = np.zeros(count, np.int32)
+    moves = np.full((count, tetrominoes, 3), -1, np.int8)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)                  # noqa: E731
+    rc = _carve().forward_generate(int(seed0), count, goal, tetrominoes, initial_height_max, max_attempts, p(rows), p(letters),
+                                   p(solvable), p(failed), p(moves), p(nmoves), int(threads or os.cpu_count() or 1))
+    if rc != 0:
+        raise ValueError("forward_generate rejected its arguments")
+    return dict(rows=rows, letters=letters, solvable=solvable, failed=failed, moves=moves, nmoves=nmoves)
+
+
+def forward_pool(L: int, M: int, start: int = 0, end: int = 100, initial_height_max: int = 4, max_attempts: int = 1000,
+                 threads: Optional[int] = None) -> ConfigPool:
+    """The reset points ``forward_warm_reset_worker`` puts on the queue (``game/tetris.py:482-488``):
+    ``translate(main.generate_batch(L, M))`` -- the winnable games among seeds ``start .. end-1`` (``main.py:35-42, 62-73``),
+    each as (board, [random.randint(0, 6)] + sequence).  Like ``translate`` (``:19-20``) the leading piece of every reset
+    point is drawn from Python's GLOBAL ``random`` stream, one draw per winnable game in seed order."""
+    import random
+    if M + 1 > MAX_PIECES:
+        raise ValueError("M + 1 pieces must fit the 42-piece queue")
+    g = forward_games(L, M, start, end - start, initial_height_max, max_attempts, threads)
+    keep = np.flatnonzero(g["solvable"])
+    pieces = np.zeros((len(keep), MAX_PIECES), np.uint8)
+    for k, j in enumerate(keep):
+        pieces[k, 0] = random.randint(0, 6)
+        pieces[k, 1:M + 1] = g["letters"][j]
+    return ConfigPool(g["rows"][keep].copy(), pieces, np.full(len(keep), M + 1, np.uint8))
 
 
 def load_pool(path: str) -> ConfigPool:

@@ -234,3 +234,22 @@ def test_all_entry_points_on_ragged_sizes(tp):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sanitize case done" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_forward_pool_feeds_the_env(tp):
+    """Reset points of the reference's forward producer (game/tetris.py:482-488) as a device-resident config pool."""
+    import random
+    random.seed(5)
+    pool = tp.forward_pool(3, 20, 0, 40, 4, 300)
+    assert pool.K > 10 and (pool.npieces == 21).all()
+    n = 1000
+    env = tp.BatchedTetris(n, 3, 20, seed=2, config_pool=pool)
+    idx = np.arange(n, dtype=np.int32) % pool.K
+    env.reset(idx=idx)
+    f = env.fields(queue=True)
+    assert np.array_equal(f["rows"].cpu().numpy(), pool.rows[idx])
+    assert np.array_equal(f["queue"].cpu().numpy()[:, :21], pool.pieces[idx, :21])
+    env.rollout_greedy(20, [760, -360, -180, -510, 100000, -100000])
+    stats = env.stats.cpu().numpy()
+    assert stats[0] > 0 and stats[1] > 0                     # the greedy policy wins some of these 3-line games
+    env.terminate()
