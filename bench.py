@@ -174,7 +174,7 @@ def run_reference(args):
         "impl": "reference", "metric": "afterstates/sec", "value": a, "unit": "afterstates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_budget * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-        "config": workload_config(args, 0),
+        "config": workload_config(args, args.envs_per_gpu * max(args.gpus, 1)),
         "env_steps_per_sec": m,
         "cpu_baseline": {"value": a, "unit": "afterstates/s", "cores": cores, "kind": "port",
                          "sample": f"oracle/piclim_oracle.py (Python restatement of game/tetris.py, one env object per episode, "
