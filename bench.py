@@ -41,6 +41,9 @@ NCU_ALU_PIPE_PCT = 66.5                       # sm__inst_executed_pipe_alu.avg.p
 NCU_ALU_PIPE_PCT_AFTERSTATES = 72.2           # same metric, stand-alone afterstates_kernel<0> (profiles/r01_ncu_full_v6_afterstates_step.txt)
 
 
+_emit = None        # set by main(): writes the JSON line to the process's real stdout
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -183,7 +186,7 @@ def run_reference(args):
                    "sample": f"oracle/piclim_oracle.c greedy rollout, {cn} envs x {cs} steps"},
         "e2e": {"value": a, "unit": "afterstates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_config(args, n_total):
@@ -211,8 +214,6 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -333,7 +334,7 @@ def run_b200(args):
 
     if world == 1:
         line.update(extra_single_gpu(tp, torch, dev, pool, args))
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if dist: dist.destroy_process_group()
 
 
@@ -390,6 +391,14 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # Rank 0 must print ONE JSON line on stdout.  Libraries write there too (NCCL's version banner comes out of C code at
+    # the first collective), so file descriptor 1 points at stderr for the whole run and the line goes to the saved one.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(text):
+        os.write(real_stdout, (text + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
