@@ -73,9 +73,25 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
                        bon, (1u << h) - 1u, (uint32_t)(20 - h), 0u};
 }
 
+// The afterstate enumeration reads the same facts once per rotation, already split into registers (no shift/mask work on
+// the ALU pipe that bounds it): three uint4 per (piece, rot)
+//   n: nb_j = -bo_j as int (-64 for j >= w)          c: cb_j, the 4-bit column images
+//   m: to bytes | cover mask | (1 << h) - 1 | 20 - h
+// w, the alias bit and n_rot are taken from the compact entry (a.x) where they are needed.
+struct OrientWide { int32_t nb[4]; uint32_t cb[4]; uint32_t to4, cover, hm, thr; };
+
+constexpr OrientWide make_wide(const OrientEntry &e) {
+    return OrientWide{{-(int32_t)(e.ay & 0xFF), -(int32_t)((e.ay >> 8) & 0xFF), -(int32_t)((e.ay >> 16) & 0xFF), -(int32_t)(e.ay >> 24)},
+                      {e.ax & 15u, (e.ax >> 4) & 15u, (e.ax >> 8) & 15u, (e.ax >> 12) & 15u},
+                      e.az, e.aw, e.by, e.bz};
+}
+
+struct OrientTable { OrientEntry e[28]; OrientWide w[28]; };
+
 // row masks top->bottom, bit j = shape column j, exactly the arrays at game/tetris.py:25-55
 #define TPL_O(a, b, c, d, n, al) make_orient(a, b, c, d, n, al)
-__constant__ OrientEntry c_orient[28] = {
+constexpr OrientTable make_table() {
+    OrientTable t{{
     // I
     TPL_O(0xF, 0, 0, 0, 2, false), TPL_O(1, 1, 1, 1, 2, false), TPL_O(0xF, 0, 0, 0, 2, true), TPL_O(1, 1, 1, 1, 2, true),
     // L
@@ -90,10 +106,15 @@ __constant__ OrientEntry c_orient[28] = {
     TPL_O(3, 6, 0, 0, 2, false), TPL_O(2, 3, 1, 0, 2, false), TPL_O(3, 6, 0, 0, 2, true), TPL_O(2, 3, 1, 0, 2, true),
     // O
     TPL_O(3, 3, 0, 0, 1, false), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true),
-};
+    }, {}};
+    for (int i = 0; i < 28; ++i) t.w[i] = make_wide(t.e[i]);
+    return t;
+}
 #undef TPL_O
+__constant__ OrientTable c_orient = make_table();
 
-constexpr int TAB_WORDS4 = 56;      // 28 entries x 2 uint4
+constexpr int TAB_COMPACT4 = 56;     // 28 entries x 2 uint4
+constexpr int TAB_WORDS4 = 56 + 84;  // + 28 wide entries x 3 uint4
 
 // `o` below is the first uint4 (a) of an entry, `ob` the second (b)
 __device__ __forceinline__ int orient_w(const uint4 &o) { return (o.x >> 16) & 7; }

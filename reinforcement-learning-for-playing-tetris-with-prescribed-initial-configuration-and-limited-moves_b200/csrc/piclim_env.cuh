@@ -103,7 +103,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
                                           uint32_t flN, uint32_t flT, int w,
                                           int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
-                                          uint32_t TO4, uint32_t cover, uint32_t hm, int thr,
+                                          uint32_t TO4, uint32_t cover, uint32_t hm, int thr, uint32_t one,
                                           uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
     if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
@@ -115,7 +115,17 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     // hard drop in height form.  nb_j = -bo_j is negated once per rotation: nvcc 12.9 / ptxas drops the operand negation when
     // it folds `H - bo` terms with a constant-zero H (the padding columns) into the 3-input VIMNMX3 (found by the GPU parity
     // tests: +64 instead of -64 won the max), so no negation is left for it to fold.
-    const int y = max(max(H[C] + nb0, H[C + 1] + nb1), __viaddmax_s32(H[C + 3], nb3, H[C + 2] + nb2));
+    // For C <= 6 all four heights are live registers: the sums H + nb are taken on the FMA pipe as H * one + nb, `one` being
+    // the value 1 from a kernel parameter -- opaque to ptxas, which would otherwise fuse each sum into an ALU-pipe
+    // VIADDMNMX -- and the four-way max is VIMNMX3 + VIMNMX: 2 ALU-pipe instructions instead of 3.
+    int y;
+    if (C <= 6) {
+        const int t0 = (int)mad_fma_pipe((uint32_t)H[C], one, (uint32_t)nb0), t1 = (int)mad_fma_pipe((uint32_t)H[C + 1], one, (uint32_t)nb1);
+        const int t2 = (int)mad_fma_pipe((uint32_t)H[C + 2], one, (uint32_t)nb2), t3 = (int)mad_fma_pipe((uint32_t)H[C + 3], one, (uint32_t)nb3);
+        y = max(max(max(t0, t1), t2), t3);
+    } else {
+        y = max(max(H[C] + nb0, H[C + 1] + nb1), __viaddmax_s32(H[C + 3], nb3, H[C + 2] + nb2));
+    }
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
     // the piece lands on empty cells, so `column | piece image` is `column + piece image`: one IMAD per window column
@@ -204,7 +214,7 @@ __device__ __forceinline__ void resolve_slot(const uint32_t (&cols)[COLS], const
 // them and resolve them with full warps (see afterstates_kernel).
 template <bool UNIFORM, class Sink>
 __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
-                                                     int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr) {
+                                                     int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr, uint32_t one = 1u) {
     if (defer) defer->mask = 0ull;
     const bool nopiece = e.head >= e.npieces;
     if (!UNIFORM && nopiece) {
@@ -256,12 +266,14 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     unsigned long long pending = 0ull, notstored = 0ull;
 
     for (int r = r_begin; r < (UNIFORM ? nrot_warp : r_end); ++r) {
-        const uint4 o = tab[(piece * 4 + r) * 2], ob = tab[(piece * 4 + r) * 2 + 1];
+        const uint4 o = tab[(piece * 4 + r) * 2];
         const int w = orient_w(o);
         int cmax_warp = 9;
         if constexpr (UNIFORM) cmax_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(COLS - w));
-        const int nb0 = -(int)(o.y & 0xFF), nb1 = -(int)((o.y >> 8) & 0xFF), nb2 = -(int)((o.y >> 16) & 0xFF), nb3 = -(int)(o.y >> 24);
-        const uint32_t cb0 = o.x & 15u, cb1 = (o.x >> 4) & 15u, cb2 = (o.x >> 8) & 15u, cb3 = (o.x >> 12) & 15u;
+        const uint4 *wide = tab + TAB_COMPACT4 + (piece * 4 + r) * 3;              // the same facts, one register each
+        const uint4 wn = wide[0], wc = wide[1], wm = wide[2];
+        const int nb0 = (int)wn.x, nb1 = (int)wn.y, nb2 = (int)wn.z, nb3 = (int)wn.w;
+        const uint32_t cb0 = wc.x, cb1 = wc.y, cb2 = wc.z, cb3 = wc.w;
         const uint32_t afl = orient_alias(o) ? F_ALIAS : 0u;
         const bool canon = afl == 0u;               // deferred slots are resolved once, from the canonical rotation
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
@@ -269,7 +281,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
         if constexpr (Sink::PACKED) sink.begin_rotation(r);
 #define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
-                                 o.z, o.w, ob.y, (int)ob.z, word, fl, pend, pmask, nsmask, cmax_warp);
+                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         if (canon) pending |= (unsigned long long)pmask << (10 * r);
@@ -304,8 +316,8 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
 
 template <class Sink>
 __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, uint32_t *scr, int ss, int L, int M, Sink &sink,
-                                                int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr) {
-    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink, r_begin, r_end, defer);
+                                                int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr, uint32_t one = 1u) {
+    afterstates_env_impl<false>(e, tab, scr, ss, L, M, sink, r_begin, r_end, defer, one);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ const char *last_error() { return g_err; }
 #define TPL_SCRATCH __shared__ uint32_t s_scr[SCR_ROWS * THREADS]; uint32_t *scr = s_scr + threadIdx.x
 
 __device__ __forceinline__ void load_table(uint4 *s_tab) {
-    if (threadIdx.x < TAB_WORDS4) s_tab[threadIdx.x] = reinterpret_cast<const uint4 *>(c_orient)[threadIdx.x];
+    for (int t = threadIdx.x; t < TAB_WORDS4; t += blockDim.x) s_tab[t] = reinterpret_cast<const uint4 *>(&c_orient)[t];
     __syncthreads();
 }
 
@@ -341,7 +341,7 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
         if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
         if (i < n) {
             GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
         }
         wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
     }
@@ -419,7 +419,7 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
     int *s_cnt = reinterpret_cast<int *>(s_orig + TILE);                            // [8] counts, [8] bases
 
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int t = tid; t < TAB_WORDS4; t += ST) s_tab[t] = reinterpret_cast<const uint4 *>(c_orient)[t];
+    for (int t = tid; t < TAB_WORDS4; t += ST) s_tab[t] = reinterpret_cast<const uint4 *>(&c_orient)[t];
     const int ntiles = (n + TILE - 1) / TILE;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = (int64_t)tile * TILE;
@@ -569,7 +569,7 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
             }
             st[3 * stride + i] = pack_meta(e);
             GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
         }
         wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
     }

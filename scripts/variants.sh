@@ -1,4 +1,4 @@
-for mb in 3 4 5 6; do
+for mb in 4 5 6; do
   TPL_NVCC_EXTRA="-DTPL_AS_MINBLOCKS=$mb" python -c "
 import importlib,sys
 sys.path.insert(0,'.')

@@ -10,7 +10,7 @@
 
 using namespace tpl;
 
-static const uint4 *table() { return reinterpret_cast<const uint4 *>(c_orient); }
+static const uint4 *table() { return reinterpret_cast<const uint4 *>(&c_orient); }
 
 struct HostSink {
     static constexpr bool PACKED = false;
