@@ -31,6 +31,19 @@ def test_every_declared_symbol_is_exported(tp):
     assert lib.tpl_abi_version() == 1
 
 
+def test_config_generator_library_exports_its_header(tp):
+    src = open(os.path.join(ROOT, "include", "piclim_configs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b((?:carve|forward)_[a-z_0-9]+)\s*\(", src)))
+    assert syms == ["carve_apply", "carve_generate", "carve_generate_from_state", "carve_pyrandom_randints", "forward_generate"]
+    lib = ctypes.CDLL(tp.build.build_carve())
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/piclim_configs.h but not exported"
+    rows = np.zeros(20, np.uint16)
+    assert lib.carve_generate(ctypes.c_uint64(0), 1, 0, 30, ctypes.c_void_p(rows.ctypes.data), None, 31, None, None, None, 1) == -1
+    assert lib.forward_generate(ctypes.c_uint64(0), 1, 3, 0, 4, 10, ctypes.c_void_p(rows.ctypes.data), None, None, None, None, None, 1) == -1
+
+
 def test_argument_errors_need_no_gpu(tp):
     L = tp._lib.lib()
     assert L.tpl_step(None, 0, 4, None, None, None, None, None, None, 1, 1, None) == -1
