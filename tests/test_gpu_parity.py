@@ -100,4 +100,4 @@ def test_compact_form_ragged_sizes(gpu, golden_dir):
 def test_fused_step_full_size_vs_oracle(gpu, golden_dir):
     """BASELINE configs[2] size: 2^20 envs through the fused kernel bench.py times, every packed feature word of all 40
     slots, every record and every counter against the C oracle (and against the three stand-alone kernels)."""
-    pc.case_fused_step_observe(gpu, _pool(golden_dir), n=1 << 20, steps=3, seed=17, env_base=1 << 33)
+    pc.case_fused_step_observe(gpu, _pool(golden_dir), n=1 << 20, steps=12, seed=17, env_base=1 << 33)
