@@ -34,10 +34,11 @@ ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out on
 # capture summarised in profiles/r01_ncu_full_v6_afterstates_step.txt (69.5 MB + 113.8 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
 NCU_TRAFFIC_AFTERSTATES_2P20 = 183.3e6
-# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v6_fused_step_observe.txt):
-# 78.2 MB read + 187.8 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
-NCU_TRAFFIC_FUSED_2P20 = 266.0e6
-NCU_ALU_PIPE_PCT = 66.5                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v6 capture)
+# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v7_fused_step_observe.txt):
+# 78.3 MB read + 187.6 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
+NCU_TRAFFIC_FUSED_2P20 = 265.8e6
+NCU_ALU_PIPE_PCT = 62.5                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v7 capture)
+NCU_ISSUE_ACTIVE_PCT = 65.5                   # smsp__issue_active.avg.pct_of_peak_sustained_active, same capture
 NCU_ALU_PIPE_PCT_AFTERSTATES = 72.2           # same metric, stand-alone afterstates_kernel<0> (profiles/r01_ncu_full_v6_afterstates_step.txt)
 
 
@@ -312,9 +313,9 @@ def run_b200(args):
                      "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
                      "traffic": NCU_TRAFFIC_FUSED_2P20 if n == (1 << 20) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_FUSED * n, "avg_launch_ms": fused_ms,
-                     "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT,
+                     "integer_pipe": {"alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT, "issue_active_pct_ncu": NCU_ISSUE_ACTIVE_PCT,
                                       "afterstates_kernel_alu_pipe_pct_of_peak_ncu": NCU_ALU_PIPE_PCT_AFTERSTATES,
-                                      "note": "the enumeration is integer(ALU)-pipe-bound, not HBM-bound (DESIGN.md section 3); "
+                                      "note": "the enumeration is bound by integer instruction issue (ALU + FMA pipes), not by HBM (DESIGN.md section 3); "
                                               "percentages are ncu sm__inst_executed_pipe_alu of peak, captures under profiles/"}},
         "kernels": {
             "note": "stand-alone kernels (3 launches per step); their sum is what the fused step replaces",
