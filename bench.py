@@ -291,6 +291,18 @@ def run_b200(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if dist: dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+    # the same call with the features left in HBM (a policy on the GPU reads them there, as train.py does): H2D actions,
+    # kernel, D2H of (rows cleared, flags, state) only
+    bufs_dev = bufs[:5] + [None, None]
+    henv.step_observe(*bufs_dev)
+    if dist: dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pin["rot"].array[:] = hrot[(2 + i) % total]; pin["loc"].array[:] = hloc[(2 + i) % total]
+        henv.step_observe(*bufs_dev)
+    e2e_dev_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist: dist.all_reduce(e2e_dev_s, op=dist.ReduceOp.MAX)
+    e2e_dev_s = float(e2e_dev_s.item())
     sampler.stop_flag = True; sampler.join(timeout=2)
     henv.close()
 
@@ -327,6 +339,11 @@ def run_b200(args):
         "e2e": {"value": n_total * 40 * e2e_steps / e2e_s, "unit": "afterstates/s", "env_steps_per_sec": n_total * e2e_steps / e2e_s,
                 "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 163 * n, "steps": e2e_steps,
                 "api": "tpl_env_step_observe (host-buffer C ABI, pinned buffers)"},
+        "e2e_features_on_device": {"value": n_total * 40 * e2e_steps / e2e_dev_s, "unit": "afterstates/s",
+                                   "env_steps_per_sec": n_total * e2e_steps / e2e_dev_s, "h2d_bytes_per_step": 2 * n,
+                                   "d2h_bytes_per_step": 3 * n, "steps": e2e_steps,
+                                   "note": "same host call with feats=NULL: the 160 B/env of features stay in HBM for a policy on the "
+                                           "GPU; not the headline e2e (that one ships every feature byte to the host)"},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
         "episode_stats": dict(zip(("episodes", "wins", "topouts", "movelimit_losses", "lines", "moves", "steps", "resets"),

@@ -174,12 +174,17 @@ int tpl_env_get_state(tpl_env *e, uint16_t *rows, uint8_t *cur, uint8_t *next, i
 int tpl_env_afterstates(tpl_env *e, uint8_t *feats, uint8_t *flags);
 /* one host-facing rollout step: H2D actions -> tpl_step_observe (move -> auto-reset of finished envs -> afterstates of
  * the new states, one kernel) -> D2H (dlines, flags, st, feats[, aflags]).  aflags == NULL selects the compact form
- * (feats byte 0 = rows cleared | flags << 3).  This is the call bench.py's e2e figure times. */
+ * (feats byte 0 = rows cleared | flags << 3).  This is the call bench.py's e2e figure times.  feats == NULL (and
+ * aflags == NULL) leaves the features on the device, see tpl_env_feats_ptr. */
 int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
                          int8_t *st, uint8_t *feats, uint8_t *aflags);
 /* pinned (page-locked) host buffers so the copies inside the calls above are true async DMA */
 void *tpl_host_alloc(int64_t bytes);
 void tpl_host_free(void *p);
+/* device pointer of the afterstate words u8[40][n][4] written by the last tpl_env_step_observe (NULL before the first
+ * one): with feats == NULL in that call the features stay in HBM for a policy that runs on the GPU and only
+ * (dlines, flags, st) are copied back. */
+void *tpl_env_feats_ptr(tpl_env *e);
 /* raw access for callers that keep data on the device (torch): device pointer of the state planes */
 void *tpl_env_state_ptr(tpl_env *e, int64_t *plane_stride);
 void *tpl_env_stream(tpl_env *e);

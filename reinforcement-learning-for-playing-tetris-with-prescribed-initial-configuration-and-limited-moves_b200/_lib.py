@@ -37,6 +37,7 @@ HOST_API = {
     "env_get_state": (c_int, [c_void_p, P, P, P, P, P, P, P, P, P]),
     "env_afterstates": (c_int, [c_void_p, P, P]),
     "env_step_observe": (c_int, [c_void_p, P, P, P, P, P, P, P]),
+    "env_feats_ptr": (c_void_p, [c_void_p]),
     "env_state_ptr": (c_void_p, [c_void_p, ctypes.POINTER(c_int64)]),
     "env_stream": (c_void_p, [c_void_p]),
     "host_alloc": (c_void_p, [c_int64]),

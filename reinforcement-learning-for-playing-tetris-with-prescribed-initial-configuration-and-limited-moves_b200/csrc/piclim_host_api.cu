@@ -239,7 +239,7 @@ int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int
     const size_t n = (size_t)e->n;
     CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
-    if (!feats) return fail(TPL_EINVAL, "tpl_env_step_observe: feats output required");
+    if (!feats && aflags) return fail(TPL_EINVAL, "tpl_env_step_observe: aflags without feats");
     RC(ensure((void **)&e->d_feats, n * 160));
     if (aflags) RC(ensure((void **)&e->d_aflags, n * 40));
     RC(tpl_step_observe(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->pool, e->K,
@@ -247,10 +247,14 @@ int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int
     if (dlines) CU(cudaMemcpyAsync(dlines, e->d_dlines, n, cudaMemcpyDeviceToHost, e->stream));
     if (flags) CU(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, e->stream));
     if (st) CU(cudaMemcpyAsync(st, e->d_st, n, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(feats, e->d_feats, n * 160, cudaMemcpyDeviceToHost, e->stream));
+    // feats == NULL: the 40-slot features stay in HBM (compact form, tpl_env_feats_ptr) for a policy that runs on the GPU;
+    // only the move's results travel back
+    if (feats) CU(cudaMemcpyAsync(feats, e->d_feats, n * 160, cudaMemcpyDeviceToHost, e->stream));
     if (aflags) CU(cudaMemcpyAsync(aflags, e->d_aflags, n * 40, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
+
+void *tpl_env_feats_ptr(tpl_env *e) { return e ? (void *)e->d_feats : nullptr; }
 
 }  // extern "C"

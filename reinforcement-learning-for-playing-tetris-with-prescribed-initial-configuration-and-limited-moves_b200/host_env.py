@@ -106,6 +106,10 @@ class HostBatchedTetris:
         _lib.check(self._L.tpl_env_move(self._h, _p(r), _p(l), _p(dl), _p(fl), _p(st)), "tpl_env_move")
         return dl, fl, st
 
+    def feats_device_ptr(self) -> int:
+        """Device address of the uint8[40, n, 4] afterstate words written by the last ``step_observe``."""
+        return int(self._L.tpl_env_feats_ptr(self._h) or 0)
+
     def fields(self, queue: bool = True) -> dict:
         n = self.num_envs
         out = dict(rows=np.empty((n, 20), np.uint16), cur=np.empty(n, np.uint8), next=np.empty(n, np.uint8),
@@ -130,9 +134,10 @@ class HostBatchedTetris:
         return feats.reshape(4, 10, n, 4).transpose(2, 0, 1, 3), flags.reshape(4, 10, n).transpose(2, 0, 1)
 
     def step_observe(self, rot: np.ndarray, loc: np.ndarray, dlines: np.ndarray, flags: np.ndarray, state: np.ndarray,
-                     feats: np.ndarray, aflags: Optional[np.ndarray]) -> None:
+                     feats: Optional[np.ndarray], aflags: Optional[np.ndarray]) -> None:
         """One host-facing rollout step into caller-provided (ideally pinned) uint8/int8 buffers:
         H2D actions -> move -> auto-reset finished envs -> afterstates -> D2H.  ``aflags=None`` selects the
-        compact form (feats byte 0 = rows cleared | flags << 3)."""
+        compact form (feats byte 0 = rows cleared | flags << 3); ``feats=None`` leaves the features on the device
+        (``feats_device_ptr()``) for a policy that runs there."""
         _lib.check(self._L.tpl_env_step_observe(self._h, _p(rot), _p(loc), _p(dlines), _p(flags), _p(state), _p(feats), _p(aflags)),
                    "tpl_env_step_observe")

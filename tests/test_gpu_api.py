@@ -151,6 +151,28 @@ def test_host_api_vs_oracle(tp, carve_pool):
         assert np.array_equal(pin["afl"].array.T, ofl)
     f = env.fields()
     assert np.array_equal(f["rows"], ost.rows) and np.array_equal(f["moves"], ost.moves)
+    # feats=None: the features stay on the device in the compact form; only the move's results come back
+    import torch
+    rot, loc = rng.integers(0, 4, n), rng.integers(0, 10, n)
+    pin["rot"].array[:] = rot; pin["loc"].array[:] = loc
+    env.step_observe(pin["rot"].array, pin["loc"].array, pin["dl"].array, pin["fl"].array, pin["st"].array, None, None)
+    odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+    assert np.array_equal(pin["dl"].array, odl) and np.array_equal(pin["st"].array, ost.state)
+    for i in np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]:
+        oep[i] += 1
+        k = po.config_index(31, 9 + int(i), int(oep[i]), carve_pool.K)
+        ost.rows[i] = carve_pool.rows[k]; ost.pieces[i] = carve_pool.pieces[k]; ost.npieces[i] = carve_pool.npieces[k]
+        ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
+    of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=8)
+    exp = of.copy(); exp[:, :, 0] |= (ofl << 3)
+    assert env.feats_device_ptr() != 0
+
+    class _DevView:                                             # zero-copy view of the library's device buffer for torch
+        __cuda_array_interface__ = {"shape": (40 * n * 4,), "typestr": "|u1", "data": (env.feats_device_ptr(), False), "version": 2}
+    dev = torch.as_tensor(_DevView(), device="cuda")
+    assert np.array_equal(dev.cpu().numpy().reshape(40, n, 4).transpose(1, 0, 2), exp)
+    with pytest.raises(tp.TplError):
+        env.step_observe(pin["rot"].array, pin["loc"].array, pin["dl"].array, pin["fl"].array, pin["st"].array, None, pin["afl"].array)
     dl, fl, st = env.move(np.zeros(n), np.zeros(n))
     feats, flags = env.afterstates()
     assert feats.shape == (n, 4, 10, 4) and flags.shape == (n, 4, 10)
