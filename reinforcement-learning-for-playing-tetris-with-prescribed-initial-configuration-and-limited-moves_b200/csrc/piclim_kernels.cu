@@ -171,7 +171,9 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
 //               2 = float4 features + flags (value-net input rows);   3 = all three.
 // All arrays are slot-major [40][n]; element (slot, i) sits at offset slot * n + i in each of them, so one
 // 32-bit offset serves every array and a warp's store of one slot is one contiguous 128-byte line.
-template <int MODE>
+// P32: the whole output array lies inside one 4 GB-aligned window (checked on the host), so advancing the store pointer by
+// one slot row is a 32-bit add on its low word -- one instruction instead of the IADD3 + IMAD.X pair of a 64-bit add.
+template <int MODE, bool P32 = false>
 struct GlobalSink {
     static constexpr bool PACKED = (MODE == 0);
     uint32_t *words; uint8_t *flags; float4 *ff;      // already offset by the env index
@@ -184,11 +186,18 @@ struct GlobalSink {
 #endif
     }
     __device__ __forceinline__ void put_packed_col(int, uint32_t packed) { *pcol = packed; }
-    // pcol += n words as ONE 64-bit multiply-add on the FMA pipe: with an immediate multiplier ptxas strength-reduces
-    // it to a LEA / LEA.HI.X pair on the ALU pipe, which is the pipe that bounds the kernel.
+    // pcol += n words.  64-bit form: ONE multiply-add by `one` (with an immediate multiplier ptxas strength-reduces it to a
+    // LEA / LEA.HI.X pair on the ALU pipe); ptxas turns it into IADD3 + IMAD.X.
     __device__ __forceinline__ void next_col() {
 #ifdef __CUDA_ARCH__
-        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(pcol) : "r"(n * 4u), "r"(one));
+        if constexpr (P32) {
+            uint32_t lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(pcol));
+            lo += n * 4u;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(pcol) : "r"(lo), "r"(hi));
+        } else {
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(pcol) : "r"(n * 4u), "r"(one));
+        }
 #endif
     }
     __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { words[(uint32_t)slot * n] = packed; }
@@ -318,7 +327,7 @@ __device__ __forceinline__ void stage_take(RecordStage &rs, Env &e) {
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
 #endif
-template <int MODE>
+template <int MODE, bool P32 = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
@@ -340,7 +349,7 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
         stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
         if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
         if (i < n) {
-            GlobalSink<MODE> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
+            GlobalSink<MODE, P32> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
             afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
         }
         wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
@@ -505,7 +514,7 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
 // One launch reads each 64-byte record once and writes it once; the memory time of the move hides under the
 // integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
 // =================================================================================================
-template <int MODE>
+template <int MODE, bool P32 = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
@@ -568,7 +577,7 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
                 st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
             }
             st[3 * stride + i] = pack_meta(e);
-            GlobalSink<MODE> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
+            GlobalSink<MODE, P32> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
             afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
         }
         wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
@@ -645,6 +654,15 @@ static bool sorted_path_ok(int n, const void *feats) {
     static int enabled = -1;
     if (enabled < 0) { const char *v = getenv("TPL_SORTED_AFTERSTATES"); enabled = (v && v[0] == '1') ? 1 : 0; }
     return enabled && n >= 2 * TILE && (n % 4) == 0 && ((uintptr_t)feats % 16) == 0;
+}
+
+// the compact output array [40][n] words does not cross a 4 GB-aligned address boundary (GlobalSink<.., P32>)
+// (TPL_NO_P32=1, read once per process, forces the 64-bit pointer chain: lets the tests cover that path too)
+static bool one_window(const void *feats, int n) {
+    static int disabled = -1;
+    if (disabled < 0) { const char *v = getenv("TPL_NO_P32"); disabled = (v && v[0] == '1') ? 1 : 0; }
+    const uintptr_t a = (uintptr_t)feats, b = a + (uintptr_t)160 * (uintptr_t)n - 1;
+    return !disabled && (a >> 32) == (b >> 32);
 }
 
 static unsigned grid_persistent(int n, int blocks_per_sm) {
@@ -745,7 +763,8 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
         else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
         return check_launch("tpl_afterstates(split)");
     }
-    if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    if (feats && !flags && one_window(feats, n)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
     else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
     else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
     else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
@@ -776,7 +795,8 @@ int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *ro
     const unsigned g = grid_persistent(n, so_blocks_per_sm);
 #define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
                                                                     seed, env_base, gen_count, w, aflags, f, L, M, 1u)
-    if (feats && !aflags) TPL_SO(0);
+    if (feats && !aflags && one_window(feats, n)) TPL_SO(0, true);
+    else if (feats && !aflags) TPL_SO(0);
     else if (feats && !feats_f32) TPL_SO(1);
     else if (!feats) TPL_SO(2);
     else TPL_SO(3);

@@ -126,3 +126,21 @@ def test_fused_step_is_deterministic(gpu, golden_dir):
     assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].state, envs[2].state)
     assert torch.equal(envs[0].episode, envs[2].episode)
     assert torch.equal(a[3], envs[2].afterstates(packed=True, raw=True)[0])
+
+
+def test_compact_form_64bit_pointer_chain(gpu, golden_dir):
+    """The compact form advances its store pointer with a 32-bit add when the output array sits inside one 4 GB window
+    (the usual case) and with a 64-bit chain otherwise; TPL_NO_P32=1 (read once per process: child) forces the latter."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests.engines import GpuEngine\n"
+            "from tests import parity_cases as pc\n"
+            "from tests.test_gpu_parity import _pool\n"
+            "g = GpuEngine()\n"
+            "pc.case_afterstates_vs_oracle(g, 100_000, 10, 30, 5)\n"
+            "pc.case_fused_step_observe(g, _pool(%r), n=50_000, steps=20)\n"
+            "print('chain64-ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir)
+    env = dict(os.environ, TPL_NO_P32="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "chain64-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
