@@ -265,6 +265,11 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
     unsigned long long pending = 0ull, notstored = 0ull;
 
+#ifndef TPL_ROT_UNROLL
+#define TPL_ROT_UNROLL 1            // tuning knob: unrolling the rotation loop was measured and does not pay
+#endif
+    constexpr int rot_unroll = TPL_ROT_UNROLL;
+#pragma unroll rot_unroll
     for (int r = r_begin; r < (UNIFORM ? nrot_warp : r_end); ++r) {
         const uint4 o = tab[(piece * 4 + r) * 2];
         const int w = orient_w(o);
