@@ -34,11 +34,11 @@ ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out on
 # capture summarised in profiles/r01_ncu_full_v6_afterstates_step.txt (69.5 MB + 113.8 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
 NCU_TRAFFIC_AFTERSTATES_2P20 = 183.3e6
-# the fused step_observe_kernel<0>, same kind of capture (profiles/r01_ncu_full_v7_fused_step_observe.txt):
-# 78.3 MB read + 187.6 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
-NCU_TRAFFIC_FUSED_2P20 = 265.8e6
-NCU_ALU_PIPE_PCT = 62.5                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v7 capture)
-NCU_ISSUE_ACTIVE_PCT = 65.5                   # smsp__issue_active.avg.pct_of_peak_sustained_active, same capture
+# the fused step_observe_kernel<0, 1>, same kind of capture (profiles/r01_ncu_full_v8_fused_step_observe.txt):
+# 78.4 MB read + 187.0 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
+NCU_TRAFFIC_FUSED_2P20 = 265.3e6
+NCU_ALU_PIPE_PCT = 62.9                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v8 capture)
+NCU_ISSUE_ACTIVE_PCT = 67.3                   # smsp__issue_active.avg.pct_of_peak_sustained_active, same capture
 NCU_ALU_PIPE_PCT_AFTERSTATES = 72.2           # same metric, stand-alone afterstates_kernel<0> (profiles/r01_ncu_full_v6_afterstates_step.txt)
 
 
@@ -321,7 +321,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, n_total),
         "env_steps_per_sec": n_total * K / (ms_total * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": "step_observe_kernel<0> (fused move + auto-reset + afterstates)",
+        "roofline": {"bound": "hbm", "kernel": "step_observe_kernel<0, 1> (fused move + auto-reset + afterstates)",
                      "achieved": fused_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fused_gbs / hbm_peak,
                      "traffic": NCU_TRAFFIC_FUSED_2P20 if n == (1 << 20) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_FUSED * n, "avg_launch_ms": fused_ms,

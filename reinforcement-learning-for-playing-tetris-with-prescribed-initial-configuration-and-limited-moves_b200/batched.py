@@ -80,6 +80,14 @@ class BatchedTetris:
         t = self._out.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, device=self.device)
+            if name == "feats":
+                # the kernels advance their store pointer with a 32-bit add when the array does not cross a 4 GB-aligned
+                # address boundary (GlobalSink<.., P32>): if this allocation happens to straddle one, take another
+                held = []
+                while (t.data_ptr() >> 32) != ((t.data_ptr() + t.numel() * t.element_size() - 1) >> 32) and len(held) < 4:
+                    held.append(t)
+                    t = torch.empty(shape, dtype=dtype, device=self.device)
+                del held
             self._out[name] = t
         return t
 

@@ -38,6 +38,23 @@ static int ensure(void **p, size_t bytes) {
     if (e != cudaSuccess) return fail((int)e, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
     return 0;
 }
+// the afterstate words: an allocation that does not cross a 4 GB-aligned address boundary lets the kernels advance their
+// store pointer with a 32-bit add (GlobalSink<.., P32>); a straddling one (rare) is swapped for another
+static int ensure_feats(tpl_env *e, size_t bytes) {
+    if (e->d_feats) return 0;
+    void *held[4]; int nheld = 0;
+    int rc = 0;
+    for (;;) {
+        void *p = nullptr;
+        rc = ensure(&p, bytes);
+        if (rc) break;
+        const uintptr_t a = (uintptr_t)p;
+        if ((a >> 32) == ((a + bytes - 1) >> 32) || nheld == 4) { e->d_feats = (uint8_t *)p; break; }
+        held[nheld++] = p;
+    }
+    for (int k = 0; k < nheld; ++k) cudaFree(held[k]);
+    return rc;
+}
 static int ensure_scratch(tpl_env *e, size_t bytes) {
     if (e->scratch_bytes >= bytes) return 0;
     if (e->d_scratch) cudaFree(e->d_scratch);
@@ -213,7 +230,7 @@ int tpl_env_get_state(tpl_env *e, uint16_t *rows, uint8_t *cur, uint8_t *next, i
 
 static int afterstates_to_host(tpl_env *e, uint8_t *feats, uint8_t *aflags) {
     const size_t n = (size_t)e->n;
-    if (feats) RC(ensure((void **)&e->d_feats, n * 160));
+    if (feats) RC(ensure_feats(e, n * 160));
     if (aflags) RC(ensure((void **)&e->d_aflags, n * 40));
     RC(tpl_afterstates(e->state, e->stride, e->n, feats ? e->d_feats : nullptr, aflags ? e->d_aflags : nullptr, nullptr, e->L, e->M,
                        e->stream));
@@ -240,7 +257,7 @@ int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int
     CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
     if (!feats && aflags) return fail(TPL_EINVAL, "tpl_env_step_observe: aflags without feats");
-    RC(ensure((void **)&e->d_feats, n * 160));
+    RC(ensure_feats(e, n * 160));
     if (aflags) RC(ensure((void **)&e->d_aflags, n * 40));
     RC(tpl_step_observe(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->pool, e->K,
                         e->episode, e->seed, e->env_base, 0, e->d_feats, aflags ? e->d_aflags : nullptr, nullptr, e->L, e->M, e->stream));
