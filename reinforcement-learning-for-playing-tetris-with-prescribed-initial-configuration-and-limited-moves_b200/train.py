@@ -69,9 +69,13 @@ class ReplayMemory:
         self.pos = (self.pos + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
-    def sample(self, batch: int, gen):
-        """-> x [B,4], r [B], done [B], nx [B,40,4], nfl [B,40]"""
-        idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
+    def sample(self, batch: int, gen, size_t: Optional[torch.Tensor] = None):
+        """-> x [B,4], r [B], done [B], nx [B,40,4], nfl [B,40].  ``size_t`` (a device scalar holding ``self.size``)
+        selects the CUDA-graph-safe index draw: no Python integer is baked into the captured kernels."""
+        if size_t is None:
+            idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
+        else:
+            idx = (torch.rand(batch, device=self.x.device) * size_t).long().clamp_(max=self.capacity - 1)
         return (self.x[idx], self.r[idx], self.done[idx], self.nx[:, idx].permute(1, 0, 2), self.nfl[:, idx].t())
 
 
@@ -95,9 +99,9 @@ class TrainStats:
         return self.env_steps / max(self.total_seconds, 1e-9)
 
 
-def select_slots(values: torch.Tensor, flags: torch.Tensor, eps: float, gen) -> torch.Tensor:
+def select_slots(values: torch.Tensor, flags: torch.Tensor, eps, gen) -> torch.Tensor:
     """Epsilon-greedy over the distinct placements: values/flags are [40, N]; alias / no-piece slots are never
-    chosen.  Returns the slot index int64[N]."""
+    chosen.  ``eps`` is a float or a device scalar tensor.  Returns the slot index int64[N]."""
     invalid = (flags & (FLAG_ALIAS | FLAG_NOPIECE)) != 0
     greedy = values.masked_fill(invalid, float("-inf")).argmax(dim=0)
     noise = torch.rand(values.shape, device=values.device, generator=gen).masked_fill(invalid, -1.0)
@@ -107,10 +111,16 @@ def select_slots(values: torch.Tensor, flags: torch.Tensor, eps: float, gen) -> 
 
 def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
           config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
-          batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True, log_fn=None) -> tuple:
+          batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True, log_fn=None,
+          cuda_graphs: bool = True) -> tuple:
     """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
     Returns (policy_net, TrainStats).  The action-selection forward pass over the 40 * num_envs afterstate rows runs
-    under bf16 autocast (it only ranks slots); the optimiser step stays fp32."""
+    under bf16 autocast (it only ranks slots); the optimiser step stays fp32.
+
+    ``cuda_graphs``: the loop is launch-bound in eager PyTorch (about 370 small launches per iteration against 3.4 ms of
+    GPU work at 65 536 envs), so after three eager iterations the two PyTorch blocks -- action selection, and the
+    `optim_steps_per_iter` optimiser steps -- are captured into CUDA graphs and replayed; the env kernel
+    (``tpl_step_observe``) and the replay push stay ordinary launches between them."""
     dev = torch.device(device)
     pool = config_pool if config_pool is not None else synthetic_pool(4096, seed=seed, M=M)
     env = BatchedTetris(num_envs, L, M, device=dev, seed=seed, config_pool=pool)
@@ -120,7 +130,9 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     policy_net = ValueNet().to(dev)
     target_net = ValueNet().to(dev)
     target_net.load_state_dict(policy_net.state_dict())
-    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True, fused=True)   # model/train.py:27 (fused: one launch)
+    use_graphs = bool(cuda_graphs) and dev.type == "cuda"
+    # model/train.py:27 (fused: one launch; capturable: its step counter lives on the device, as graph capture needs)
+    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True, fused=True, capturable=use_graphs)
     p_params, t_params = list(policy_net.parameters()), list(target_net.parameters())
     loss_fn = nn.SmoothL1Loss()
     memory = ReplayMemory(replay_capacity, dev)
@@ -128,52 +140,90 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     ar = torch.arange(num_envs, device=dev)
     t_all = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env_events, last_loss, prev_stats = [], None, {}
+    env_events, prev_stats = [], {}
+    eps_t = torch.zeros((), device=dev)                     # epsilon and the replay fill level as device scalars: graph inputs
+    size_t = torch.zeros((), device=dev)
+    last_loss = torch.full((), float("nan"), device=dev)
+    g_gen = None if use_graphs else gen                      # captured regions draw from the default CUDA generator
 
-    feats, flags, ff = env.afterstates(f32=True, raw=True)  # slot-major: [40,N,4] u8, [40,N] u8, [40N,4] f32
-    for it in range(iterations):
-        eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference):
+    feats, flags, ff = env.afterstates(f32=True, raw=True)  # slot-major: [40,N,4] u8, [40,N] u8, [40N,4] f32 (static buffers)
+    act_out = {}
+
+    def act_block():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference, cache_enabled=not use_graphs):
             values = policy_net(ff).float().view(40, num_envs)
         with torch.no_grad():
-            slot = select_slots(reward_from(feats[..., 0], flags) + GAMMA * values, flags, eps, gen)
-        rot, loc = (slot // 10).to(torch.uint8), (slot % 10).to(torch.uint8)
-        x = feats[slot, ar].clone()                                                 # chosen afterstate features [N,4]
+            slot = select_slots(reward_from(feats[..., 0], flags) + GAMMA * values, flags, eps_t, g_gen)
+            rot, loc = (slot // 10).to(torch.uint8), (slot % 10).to(torch.uint8)
+            x = feats[slot, ar].clone()                                             # chosen afterstate features [N,4]
+        for k, v in (("rot", rot), ("loc", loc), ("x", x)):
+            if k in act_out: act_out[k].copy_(v)
+            else: act_out[k] = v.clone()
+
+    def optim_block():
+        for _ in range(optim_steps_per_iter):
+            bx, br, bdone, bnx, bnfl = memory.sample(batch_size, g_gen, size_t if use_graphs else None)
+            with torch.no_grad():
+                nv = target_net(bnx.reshape(-1, 4)).view(batch_size, 40)
+                nr = reward_from(bnx[..., 0], bnfl)
+                q = (nr + GAMMA * nv * ((bnfl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
+                    (bnfl & (FLAG_ALIAS | FLAG_NOPIECE)) != 0, float("-inf"))
+                best_next = q.max(dim=1).values
+                # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal)
+                target = torch.where(bdone, torch.zeros_like(best_next), best_next)
+            loss = loss_fn(policy_net(bx), target)
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_value_(p_params, 100, foreach=True)
+            optimizer.step()
+            with torch.no_grad():                                               # soft update, TAU (two foreach launches)
+                torch._foreach_mul_(t_params, 1 - TAU)
+                torch._foreach_add_(t_params, p_params, alpha=TAU)
+        last_loss.copy_(loss.detach())
+
+    def run_or_capture(block, graph, it):
+        """eager for the first iterations; then once more on a side stream (what capture wants) and captured; then replayed"""
+        if graph is not None:
+            graph.replay()
+            return graph
+        if not use_graphs or it < 3:
+            block()
+            return None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            block()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            block()
+        return g
+
+    g_act = g_opt = None
+    for it in range(iterations):
+        eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
+        eps_t.fill_(eps)
+        g_act = run_or_capture(act_block, g_act, it)
+        x = act_out["x"]
         ev0.record()
         # one launch: move -> auto-reset of finished episodes -> afterstates of the new states (tpl_step_observe)
-        dlines, mflags, state, feats, flags, ff = env.step_observe(rot, loc, packed=False, f32=True)
+        dlines, mflags, state, feats2, flags2, ff2 = env.step_observe(act_out["rot"], act_out["loc"], packed=False, f32=True)
+        assert feats2.data_ptr() == feats.data_ptr() and ff2.data_ptr() == ff.data_ptr()     # the env reuses its output buffers
         reward = reward_from(dlines, mflags)
         done = state != 0
         ev1.record()
         memory.push(x, reward, done, feats, flags)
+        size_t.fill_(float(memory.size))
         st.env_steps += num_envs
         if memory.size >= batch_size:
-            for _ in range(optim_steps_per_iter):
-                bx, br, bdone, bnx, bnfl = memory.sample(batch_size, gen)
-                with torch.no_grad():
-                    nv = target_net(bnx.reshape(-1, 4)).view(batch_size, 40)
-                    nr = reward_from(bnx[..., 0], bnfl)
-                    q = (nr + GAMMA * nv * ((bnfl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
-                        (bnfl & (FLAG_ALIAS | FLAG_NOPIECE)) != 0, float("-inf"))
-                    best_next = q.max(dim=1).values
-                    # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal)
-                    target = torch.where(bdone, torch.zeros_like(best_next), best_next)
-                loss = loss_fn(policy_net(bx), target)
-                optimizer.zero_grad(set_to_none=True)
-                loss.backward()
-                torch.nn.utils.clip_grad_value_(p_params, 100, foreach=True)
-                optimizer.step()
-                with torch.no_grad():                                               # soft update, TAU (two foreach launches)
-                    torch._foreach_mul_(t_params, 1 - TAU)
-                    torch._foreach_add_(t_params, p_params, alpha=TAU)
-                st.optim_steps += 1
-            last_loss = loss.detach()
+            g_opt = run_or_capture(optim_block, g_opt, it)
+            st.optim_steps += optim_steps_per_iter
         env_events.append((ev0, ev1))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st.eps = eps
         if log_every and (it + 1) % log_every == 0:
             s = env.reduce_stats()
-            st.loss = float(last_loss.item()) if last_loss is not None else float("nan")
+            st.loss = float(last_loss.item())
             if log_fn is not None:
                 log_fn(it + 1, eps, st.loss, s, prev_stats)
                 prev_stats = dict(s)
@@ -183,7 +233,7 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     torch.cuda.synchronize(dev)
     st.total_seconds = time.perf_counter() - t_all
     st.env_seconds = sum(a.elapsed_time(b) for a, b in env_events) * 1e-3
-    st.loss = float(last_loss.item()) if last_loss is not None else float("nan")
+    st.loss = float(last_loss.item())
     s = env.reduce_stats()
     st.episodes, st.wins = s["episodes"], s["wins"]
     return policy_net, st
