@@ -31,15 +31,15 @@ ALG_BYTES_AFTERSTATES = 64 + 40 * 4           # read one 64 B record, write 40 x
 ALG_BYTES_STEP = 64 + 2 + 64 + 3              # record in, action in, record out, (dlines, flags, state) out
 ALG_BYTES_FUSED = 64 + 2 + 64 + 3 + 40 * 4    # the fused step: record in/out once, action, results, 40 packed feature words
 # dram__bytes_read.sum + dram__bytes_write.sum of one afterstates_kernel<0> launch at 2^20 envs, from the ncu --set full
-# capture summarised in profiles/r01_ncu_full_v6_afterstates_step.txt (69.5 MB + 113.8 MB; the rest of the 160 MiB of
+# capture summarised in profiles/r01_ncu_full_v8_afterstates_step.txt (69.9 MB + 115.0 MB; the rest of the 160 MiB of
 # output is still in L2 when the kernel ends)
-NCU_TRAFFIC_AFTERSTATES_2P20 = 183.3e6
+NCU_TRAFFIC_AFTERSTATES_2P20 = 184.9e6
 # the fused step_observe_kernel<0, 1>, same kind of capture (profiles/r01_ncu_full_v8_fused_step_observe.txt):
 # 78.4 MB read + 187.0 MB write per launch against 307 MB algorithmic (the tail of the writes is still in L2)
 NCU_TRAFFIC_FUSED_2P20 = 265.3e6
 NCU_ALU_PIPE_PCT = 62.9                       # sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active, fused kernel (v8 capture)
 NCU_ISSUE_ACTIVE_PCT = 67.3                   # smsp__issue_active.avg.pct_of_peak_sustained_active, same capture
-NCU_ALU_PIPE_PCT_AFTERSTATES = 72.2           # same metric, stand-alone afterstates_kernel<0> (profiles/r01_ncu_full_v6_afterstates_step.txt)
+NCU_ALU_PIPE_PCT_AFTERSTATES = 67.2           # same metric, stand-alone afterstates_kernel<0, 1> (profiles/r01_ncu_full_v8_afterstates_step.txt; issue-active 71 %)
 
 
 _emit = None        # set by main(): writes the JSON line to the process's real stdout
