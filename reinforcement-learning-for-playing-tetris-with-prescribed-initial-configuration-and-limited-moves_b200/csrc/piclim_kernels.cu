@@ -221,7 +221,11 @@ struct GlobalSink {
 // resolved by a full warp.  No __syncthreads in the tile loop at all: the 16 resident warps of an SM drift freely and
 // cover each other's load latency.
 constexpr int WQ_ENVS = 64;          // env entries: < 32 live after a resolve + <= 32 new per tile
-constexpr int WQ_ITEMS = 512;        // deferred slots; a lane whose slots do not fit resolves them itself (never seen in practice)
+#ifndef TPL_WQ_ITEMS
+#define TPL_WQ_ITEMS 512             // (-DTPL_WQ_ITEMS=40 makes the overflow path below run all the time: used once to validate it)
+#endif
+constexpr int WQ_ITEMS = TPL_WQ_ITEMS;   // deferred slots (>= 40); a lane whose slots do not fit resolves them itself (never seen in practice)
+static_assert(WQ_ITEMS >= 40, "room for the < 32 live items plus at least a few new ones");
 struct WarpQueue {
     uint32_t env[13 * WQ_ENVS];      // [k][entry]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines, env index
     uint16_t items[WQ_ITEMS];        // entry | slot << 6
