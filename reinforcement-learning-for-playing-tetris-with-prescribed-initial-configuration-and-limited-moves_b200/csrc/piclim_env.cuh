@@ -97,7 +97,7 @@ __device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, ui
     return s;
 }
 
-template <int C, class Sink>
+template <int C, bool UNIFORM, class Sink>
 __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14], const uint32_t (&Hw)[COLS],
                                           const uint32_t (&col)[14],
                                           const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
@@ -105,7 +105,9 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO4, uint32_t cover, uint32_t hm, int thr, uint32_t one,
                                           uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
-    if (C > 6 && C > cmax_warp) {                  // no lane of this warp fits a shape at column C: only the clamp alias
+    // No lane of this warp fits a shape at column C: only the clamp alias.  Without piece-sorted warps (UNIFORM) that is known
+    // statically for column 9 of rotations 0 and 2, where the narrowest shape of any piece is two wide (cmax_warp = 8).
+    if (UNIFORM ? (C > 6 && C > cmax_warp) : (C == 9 && cmax_warp < 9)) {
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
         else { fl |= F_ALIAS; if (!pend) sink.put(r * 10 + C, word, fl); }
         if (pend) nsmask |= 1u << C;
@@ -273,7 +275,8 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     for (int r = r_begin; r < (UNIFORM ? nrot_warp : r_end); ++r) {
         const uint4 o = tab[(piece * 4 + r) * 2];
         const int w = orient_w(o);
-        int cmax_warp = 9;
+        // widest reach of any piece in this rotation: the only one-wide shape is the vertical I, rotations 1 and 3 (game/tetris.py:25-55)
+        int cmax_warp = (r & 1) ? 9 : 8;
         if constexpr (UNIFORM) cmax_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(COLS - w));
         const uint4 *wide = tab + TAB_COMPACT4 + (piece * 4 + r) * 3;              // the same facts, one register each
         const uint4 wn = wide[0], wc = wide[1], wm = wide[2];
@@ -285,7 +288,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const uint32_t Kr = Sink::PACKED ? K + (flN << 3) : K, Ur = Sink::PACKED ? (U | (flT << 3)) : U;
         uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
         if constexpr (Sink::PACKED) sink.begin_rotation(r);
-#define TPL_SLOT(C) slot_fast<C>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
+#define TPL_SLOT(C) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
                                  wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
