@@ -150,8 +150,11 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     act_out = {}
 
     def act_block():
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference, cache_enabled=not use_graphs):
-            values = policy_net(ff).float().view(40, num_envs)
+        if bf16_inference and hasattr(torch, "_addmm_activation"):
+            values = policy_net.rank_bf16(ff).float().view(40, num_envs)        # GEMMs with fused bias + ReLU epilogues
+        else:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16_inference, cache_enabled=not use_graphs):
+                values = policy_net(ff).float().view(40, num_envs)
         with torch.no_grad():
             slot = select_slots(reward_from(feats[..., 0], flags) + GAMMA * values, flags, eps_t, g_gen)
             rot, loc = (slot // 10).to(torch.uint8), (slot % 10).to(torch.uint8)

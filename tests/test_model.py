@@ -17,6 +17,8 @@ def test_model_matches_reference_layer_shape():
     assert net(torch.zeros(3, 217)).shape == (3, 14)
     v = m.ValueNet()
     assert v(torch.zeros(5, 4, dtype=torch.uint8)).shape == (5,)
+    x = torch.randint(0, 200, (64, 4)).to(torch.float32)
+    assert torch.allclose(v.rank_bf16(x).float(), v(x), atol=0.05, rtol=0.05)      # bf16 ranking forward == fp32 forward (loosely)
 
 
 def test_hyperparameters_are_the_reference_ones():
