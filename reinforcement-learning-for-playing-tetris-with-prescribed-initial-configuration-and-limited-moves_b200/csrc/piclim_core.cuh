@@ -189,6 +189,26 @@ __device__ __forceinline__ uint32_t mad_fma_pipe(uint32_t a, uint32_t b, uint32_
 #endif
 }
 
+// two-way dot products of s16 pairs with u8 pairs (IDP.2A): a.lo * b.byte0 + a.hi * b.byte1 + c, resp. bytes 2 and 3
+__device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c) {
+#ifdef TPL_HOST_EMUL
+    return (int)(int16_t)(a & 0xFFFFu) * (int)(b & 0xFFu) + (int)(int16_t)(a >> 16) * (int)((b >> 8) & 0xFFu) + c;
+#else
+    int r;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));       // signed halves of a, unsigned bytes of b
+    return r;
+#endif
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) {
+#ifdef TPL_HOST_EMUL
+    return (int)(int16_t)(a & 0xFFFFu) * (int)((b >> 16) & 0xFFu) + (int)(int16_t)(a >> 16) * (int)(b >> 24) + c;
+#else
+    int r;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#endif
+}
+
 // a * b on the FMA pipe (IMAD): used for `bits << y` as bits * (1 << y) so the variable shifts do not all
 // land on the ALU pipe, which is the pipe that bounds the afterstate kernel
 __device__ __forceinline__ uint32_t mul_fma_pipe(uint32_t a, uint32_t b) {

@@ -356,21 +356,32 @@ __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32
 //   value = w[0]*dlines + w[1]*holes + w[2]*bumpiness + w[3]*agg_height + (win ? w[4] : 0)
 //           + (lose or top-out ? w[5] : 0)
 // ---------------------------------------------------------------------------------------------
-struct GreedySink {
+// W16: the four feature weights fit int16, so the value of a slot is two dot-product instructions on the packed feature word
+// (IDP.2A: two s16 weights x two u8 features each) instead of four byte extractions and four multiply-adds.
+template <bool W16>
+struct GreedySinkT {
     static constexpr bool PACKED = false;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
-        int v = w0 * (int)(word & 0xFFu) + w1 * (int)((word >> 8) & 0xFFu) + w2 * (int)((word >> 16) & 0xFFu) +
+        int v;
+        if constexpr (W16) {
+            v = dp2a_hi((uint32_t)w2 & 0xFFFFu | ((uint32_t)w3 << 16), word, dp2a_lo((uint32_t)w0 & 0xFFFFu | ((uint32_t)w1 << 16), word, 0));
+        } else {
+            v = w0 * (int)(word & 0xFFu) + w1 * (int)((word >> 8) & 0xFFu) + w2 * (int)((word >> 16) & 0xFFu) +
                 w3 * (int)(word >> 24);
+        }
         if (fl & F_WIN) v += w4;
         if (fl & (F_LOSE | F_TOPOUT)) v += w5;
         if (v > best || (v == best && slot < best_slot)) { best = v; best_slot = slot; }
     }
 };
 
+using GreedySink = GreedySinkT<false>;
+
 struct GreedyWeights { int w[6]; };
 
+template <bool W16 = false>
 __device__ __forceinline__ void rollout_greedy_step(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
                                                     uint32_t *scr, int ss, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
                                                     int gen_count, int L, int M, const GreedyWeights &gw) {
@@ -378,7 +389,7 @@ __device__ __forceinline__ void rollout_greedy_step(Env &e, uint32_t &ep, uint32
         ep += 1; t = 0; acc[7] += 1;
         install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
     }
-    GreedySink sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};
+    GreedySinkT<W16> sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};
     afterstates_env(e, tab, scr, ss, L, M, sink);
     const int slot = sink.best_slot < 40 ? sink.best_slot : 0;
     const uint32_t rot = (uint32_t)(slot / 10), loc = (uint32_t)(slot - 10 * (slot / 10));

@@ -606,8 +606,11 @@ gen_pieces_kernel(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_ba
 // =================================================================================================
 // fused rollouts: state stays in registers for `steps` moves
 // =================================================================================================
-template <bool GREEDY>
-__global__ void __launch_bounds__(THREADS)
+#ifndef TPL_RO_MINBLOCKS
+#define TPL_RO_MINBLOCKS 4          // 128 registers (unconstrained the greedy variant takes 161: 12 warps per SM)
+#endif
+template <int POLICY>               // 0 random agent, 1 greedy (int32 weights), 2 greedy with int16 feature weights (dot-product form)
+__global__ void __launch_bounds__(THREADS, POLICY == 0 ? 7 : TPL_RO_MINBLOCKS)      // the random agent needs 66 registers only
 rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, int K, uint32_t *episode,
                uint32_t *tstep, unsigned long long *stats, int steps, uint64_t seed, uint64_t env_base,
                int gen_count, int L, int M, GreedyWeights gw) {
@@ -621,7 +624,8 @@ rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool,
         Env e; load_env(st, stride, i, e);
         uint32_t ep = episode[i], t = tstep[i];
         for (int s = 0; s < steps; ++s) {
-            if (GREEDY) rollout_greedy_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
+            if (POLICY == 2) rollout_greedy_step<true>(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
+            else if (POLICY == 1) rollout_greedy_step<false>(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
             else rollout_random_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M);
         }
         store_env(st, stride, i, e);
@@ -827,14 +831,14 @@ static int rollout_common(const char *who, bool greedy, void *state, int64_t pla
     if (n == 0 || steps <= 0) return 0;
     GreedyWeights gw{};
     if (greedy) for (int q = 0; q < 6; ++q) gw.w[q] = w6[q];
-    if (greedy)
-        rollout_kernel<true><<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, (const uint4 *)pool, K, episode,
-                                                                               tstep, (unsigned long long *)stats, steps, seed, env_base,
-                                                                               gen_count, L, M, gw);
-    else
-        rollout_kernel<false><<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, (const uint4 *)pool, K, episode,
-                                                                                tstep, (unsigned long long *)stats, steps, seed, env_base,
-                                                                                gen_count, L, M, gw);
+    bool w16 = greedy;
+    for (int q = 0; greedy && q < 4; ++q) w16 = w16 && gw.w[q] >= -32768 && gw.w[q] <= 32767;
+#define TPL_RO(P) rollout_kernel<P><<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, (const uint4 *)pool, K, \
+                                episode, tstep, (unsigned long long *)stats, steps, seed, env_base, gen_count, L, M, gw)
+    if (w16) TPL_RO(2);
+    else if (greedy) TPL_RO(1);
+    else TPL_RO(0);
+#undef TPL_RO
     return check_launch(who);
 }
 
