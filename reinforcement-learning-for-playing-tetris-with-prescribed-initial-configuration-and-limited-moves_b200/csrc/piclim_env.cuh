@@ -359,22 +359,35 @@ __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32
 // W16: the four feature weights fit int16, so the value of a slot is two dot-product instructions on the packed feature word
 // (IDP.2A: two s16 weights x two u8 features each) instead of four byte extractions and four multiply-adds.
 template <bool W16>
+__device__ __forceinline__ int greedy_value(int w0, int w1, int w2, int w3, int w4, int w5, uint32_t word, uint32_t fl) {
+    int v;
+    if constexpr (W16) {
+        v = dp2a_hi((uint32_t)w2 & 0xFFFFu | ((uint32_t)w3 << 16), word, dp2a_lo((uint32_t)w0 & 0xFFFFu | ((uint32_t)w1 << 16), word, 0));
+    } else {
+        v = w0 * (int)(word & 0xFFu) + w1 * (int)((word >> 8) & 0xFFu) + w2 * (int)((word >> 16) & 0xFFu) +
+            w3 * (int)(word >> 24);
+    }
+    if (fl & F_WIN) v += w4;
+    if (fl & (F_LOSE | F_TOPOUT)) v += w5;
+    return v;
+}
+
+template <bool W16>
 struct GreedySinkT {
     static constexpr bool PACKED = false;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
-        int v;
-        if constexpr (W16) {
-            v = dp2a_hi((uint32_t)w2 & 0xFFFFu | ((uint32_t)w3 << 16), word, dp2a_lo((uint32_t)w0 & 0xFFFFu | ((uint32_t)w1 << 16), word, 0));
-        } else {
-            v = w0 * (int)(word & 0xFFu) + w1 * (int)((word >> 8) & 0xFFu) + w2 * (int)((word >> 16) & 0xFFu) +
-                w3 * (int)(word >> 24);
-        }
-        if (fl & F_WIN) v += w4;
-        if (fl & (F_LOSE | F_TOPOUT)) v += w5;
+        const int v = greedy_value<W16>(w0, w1, w2, w3, w4, w5, word, fl);
         if (v > best || (v == best && slot < best_slot)) { best = v; best_slot = slot; }
     }
+};
+
+// records the first put only: resolve_slot stores the canonical slot first, its aliases (equal value, higher index) after
+struct FirstPutSink {
+    static constexpr bool PACKED = false;
+    uint32_t word, fl; bool got;
+    __device__ __forceinline__ void put(int, uint32_t w, uint32_t f) { if (!got) { word = w; fl = f; got = true; } }
 };
 
 using GreedySink = GreedySinkT<false>;

@@ -606,6 +606,87 @@ gen_pieces_kernel(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_ba
 // =================================================================================================
 // fused rollouts: state stays in registers for `steps` moves
 // =================================================================================================
+// ---- greedy policy: the deferred (row-completing) slots of a step are pooled over the warp ---------------------------------
+// The arg-max needs every slot's value before the move, so the deferred slots cannot wait for later tiles as in the
+// afterstate kernels.  Resolved in place, the warp runs the general move once per deferred slot of its BUSIEST lane while
+// the other lanes idle; pooled, the (lane, slot) items of the whole warp are dealt out to consecutive lanes and one round
+// usually covers them all.  Results come back to the owner through a 64-bit atomicMax on (value, lowest slot).
+struct GreedyPool {
+    uint32_t env[12 * 32];                         // [k][lane]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines
+    uint16_t items[40 * 32];                       // owner lane | slot << 5
+    unsigned long long key[32];
+};
+__device__ __forceinline__ unsigned long long greedy_key(int v, int slot) {
+    return ((unsigned long long)((uint32_t)v ^ 0x80000000u) << 8) | (unsigned long long)(255 - slot);
+}
+
+template <bool W16>
+__device__ __forceinline__ void rollout_greedy_step_pooled(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
+                                                           uint32_t *scr, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
+                                                           int gen_count, int L, int M, const GreedyWeights &gw, GreedyPool &gp, bool valid) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (valid && (e.state != S_RUNNING || e.head >= e.npieces)) {
+        ep += 1; t = 0; acc[7] += 1;
+        install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
+    }
+    GreedySinkT<W16> sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};
+    PendingCtx cx; cx.mask = 0ull;
+    if (valid) afterstates_env(e, tab, scr, THREADS, L, M, sink, 0, 4, &cx);
+    const uint32_t cnt = (uint32_t)__popcll(cx.mask);
+    if (__ballot_sync(0xFFFFFFFFu, cnt != 0u)) {
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        gp.key[lane] = 0ull;
+        if (cnt) {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) gp.env[k * 32 + lane] = e.col[k];
+            gp.env[10 * 32 + lane] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
+            gp.env[11 * 32 + lane] = cx.lines;
+            unsigned long long m = cx.mask;
+            uint32_t at = incl - cnt;
+            while (m) {
+                const int sl = __ffsll((long long)m) - 1;
+                m &= m - 1ull;
+                gp.items[at++] = (uint16_t)(lane | ((uint32_t)sl << 5));
+            }
+        }
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t k = base + lane;
+            if (k < total) {
+                const uint32_t item = gp.items[k], owner = item & 31u, slot = item >> 5;
+                uint32_t cols[COLS];
+#pragma unroll
+                for (int j = 0; j < COLS; ++j) cols[j] = gp.env[j * 32 + owner];
+                const uint32_t m0 = gp.env[10 * 32 + owner];
+                const PendingCtx c2{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, gp.env[11 * 32 + owner], m0 >> 16};
+                FirstPutSink fs{0u, 0u, false};
+                resolve_slot(cols, c2, (int)slot, tab, scr, THREADS, L, fs);
+                const int v = greedy_value<W16>(gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], fs.word, fs.fl);
+                atomicMax(&gp.key[owner], greedy_key(v, (int)slot));
+            }
+        }
+        __syncwarp();
+        const unsigned long long mine = gp.key[lane];
+        if (mine > greedy_key(sink.best, sink.best_slot)) sink.best_slot = 255 - (int)(mine & 255ull);
+        __syncwarp();                                  // the pool is reused by the next step
+    }
+    if (valid) {
+        const int slot = sink.best_slot < 40 ? sink.best_slot : 0;
+        const uint32_t rot = (uint32_t)(slot / 10), loc = (uint32_t)(slot - 10 * (slot / 10));
+        int k; bool changed;
+        const uint32_t fl = step_env(e, tab, scr, THREADS, rot, loc, L, M, k, changed);
+        t += 1;
+        acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
+        if (e.state != S_RUNNING) {
+            acc[0] += 1;
+            if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+        }
+    }
+}
+
 #ifndef TPL_RO_MINBLOCKS
 #define TPL_RO_MINBLOCKS 4          // 128 registers (unconstrained the greedy variant takes 161: 12 warps per SM)
 #endif
@@ -615,19 +696,22 @@ rollout_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool,
                uint32_t *tstep, unsigned long long *stats, int steps, uint64_t seed, uint64_t env_base,
                int gen_count, int L, int M, GreedyWeights gw) {
     __shared__ uint4 s_tab[TAB_WORDS4];
+    __shared__ GreedyPool s_gp[POLICY == 0 ? 1 : THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
     const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    const bool valid = i < n;
+    const int64_t ic = valid ? i : (int64_t)n - 1;                       // lanes past the end shadow the last env and store nothing
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (i < n) {
-        const uint64_t env = env_base + (uint64_t)i;
-        Env e; load_env(st, stride, i, e);
-        uint32_t ep = episode[i], t = tstep[i];
-        for (int s = 0; s < steps; ++s) {
-            if (POLICY == 2) rollout_greedy_step<true>(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
-            else if (POLICY == 1) rollout_greedy_step<false>(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M, gw);
-            else rollout_random_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M);
-        }
+    const uint64_t env = env_base + (uint64_t)ic;
+    Env e; load_env(st, stride, ic, e);
+    uint32_t ep = episode[ic], t = tstep[ic];
+    for (int s = 0; s < steps; ++s) {
+        if (POLICY == 2) rollout_greedy_step_pooled<true>(e, ep, t, acc, s_tab, scr, pool, K, seed, env, gen_count, L, M, gw, s_gp[threadIdx.x >> 5], valid);
+        else if (POLICY == 1) rollout_greedy_step_pooled<false>(e, ep, t, acc, s_tab, scr, pool, K, seed, env, gen_count, L, M, gw, s_gp[threadIdx.x >> 5], valid);
+        else if (valid) rollout_random_step(e, ep, t, acc, s_tab, scr, THREADS, pool, K, seed, env, gen_count, L, M);
+    }
+    if (valid) {
         store_env(st, stride, i, e);
         episode[i] = ep; tstep[i] = t;
     }
