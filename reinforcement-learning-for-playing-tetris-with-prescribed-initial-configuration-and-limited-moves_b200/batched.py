@@ -307,6 +307,25 @@ class BatchedTetris:
             dist.all_reduce(s, op=dist.ReduceOp.SUM)
         return dict(zip(STAT_NAMES, (int(v) for v in s.tolist())))
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> dict:
+        """Everything a rollout continues from: the env records, per-env episode / step counters, the statistics and the
+        keys of the counter RNG.  (The reference has no persistence; its env state is Python objects.  Here it is four flat
+        tensors, so ``torch.save(env.state_dict(), path)`` is a checkpoint.)  The config pool is not included."""
+        return {"state": self.state.clone(), "episode": self.episode.clone(), "tstep": self.tstep.clone(),
+                "stats": self.stats.clone(),
+                "meta": {"num_envs": self.num_envs, "L": self.L, "M": self.M, "seed": self.seed, "env_base": self.env_base,
+                         "gen_count": self.gen_count, "stride": self.stride}}
+
+    def load_state_dict(self, d: dict) -> None:
+        m = d["meta"]
+        if (m["num_envs"], m["stride"]) != (self.num_envs, self.stride):
+            raise ValueError(f"checkpoint holds {m['num_envs']} envs, this object {self.num_envs}")
+        self.L, self.M, self.seed = int(m["L"]), int(m["M"]), int(m["seed"])
+        self.env_base, self.gen_count = int(m["env_base"]), int(m["gen_count"])
+        for k in ("state", "episode", "tstep", "stats"):
+            getattr(self, k).copy_(d[k].to(self.device))
+
     def terminate(self) -> None:
         """API parity with ``Tetris.terminate`` (``game/tetris.py:451``): there are no worker processes to join."""
         return None

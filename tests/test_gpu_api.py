@@ -275,3 +275,27 @@ def test_forward_pool_feeds_the_env(tp):
     stats = env.stats.cpu().numpy()
     assert stats[0] > 0 and stats[1] > 0                     # the greedy policy wins some of these 3-line games
     env.terminate()
+
+
+def test_checkpoint_resume(tp, carve_pool, tmp_path):
+    """state_dict -> torch.save -> load_state_dict into a fresh object continues the rollout bit for bit (records, episode
+    counters, counter-RNG position, statistics)."""
+    import torch
+    n = 20_000
+    a = tp.BatchedTetris(n, 10, 30, seed=5, config_pool=carve_pool, env_base=3)
+    a.reset(); a.rollout_random(25); a.rollout_greedy(5, [760, -360, -180, -510, 100000, -100000])
+    path = os.path.join(tmp_path, "ckpt.pt")
+    torch.save(a.state_dict(), path)
+    a.rollout_random(30)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    rot = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+    loc = torch.randint(0, 10, (n,), device="cuda", dtype=torch.uint8, generator=g)
+    ra = a.step_observe(rot, loc, packed=True)
+    b = tp.BatchedTetris(n, 1, 1, seed=0, config_pool=carve_pool)          # different L / M / seed: all restored
+    b.load_state_dict(torch.load(path))
+    b.rollout_random(30)
+    rb = b.step_observe(rot, loc, packed=True)
+    assert torch.equal(a.state, b.state) and torch.equal(a.episode, b.episode) and torch.equal(a.stats, b.stats)
+    assert torch.equal(ra[3], rb[3]) and (b.L, b.M, b.seed, b.env_base) == (10, 30, 5, 3)
+    with pytest.raises(ValueError):
+        tp.BatchedTetris(n + 1, 10, 30, config_pool=carve_pool).load_state_dict(torch.load(path))
