@@ -34,6 +34,15 @@
  *   feats  uint8[40][n][4] = (rows cleared, holes, bumpiness, aggregate height)
  *   flags  uint8[40][n]    = TPL_FLAG_* bits
  *   feats_f32 float[40][n][4] (optional) = the same four numbers as floats (value-net input rows)
+ * Distinct-placements form (tpl_*_distinct): the 40-slot grid aliases by rot % n_rot (:61) and min(loc, 10 - w) (:364), so
+ *   only 9 (O), 17 (I, S, Z) or 34 (L, J, T) of the 40 slots differ -- 23.1 on average.  This form writes exactly those:
+ *   rows  uint32[...]  one word per distinct placement, byte 0 = rows cleared | flags << 3, then holes, bumpiness, aggregate
+ *                      height (the compact form's word; TPL_FLAG_ALIAS never set).  The placements of one env are contiguous
+ *                      ("run"), ordered by rotation r < n_rot, then column c <= 10 - w.
+ *   runs  uint32[n]    run descriptor of env i: TPL_RUN_OFFSET = word offset of its run in rows, TPL_RUN_PIECE = its current
+ *                      piece, which fixes the run's length and the (rot, loc) of each placement (tpl_distinct_tables).
+ *   Runs of a 32-env tile are adjacent; tiles are placed by an atomic counter, so their order in rows is unspecified (and
+ *   may differ between runs of the same program); tiles start 16-byte aligned, gaps (< 4 words) hold zeros.
  */
 #ifndef TETRIS_PICLIM_H_
 #define TETRIS_PICLIM_H_
@@ -44,9 +53,14 @@
 extern "C" {
 #endif
 
-#define TPL_ABI_VERSION 1
+#define TPL_ABI_VERSION 2
 #define TPL_MAX_PIECES 42
 #define TPL_RECORD_BYTES 64
+/* distinct-placements ("alias-free") afterstate form: at most 34 placements per env (L, J, T), see tpl_afterstates_distinct */
+#define TPL_DISTINCT_MAX 34
+#define TPL_DISTINCT_CAPACITY(n) (34 * (int64_t)(n) + 4 * (((int64_t)(n) + 31) / 32))   /* words the rows array must hold */
+#define TPL_RUN_OFFSET(d) ((d) & 0x1FFFFFFFu)   /* run descriptor -> word offset of the env's first placement */
+#define TPL_RUN_PIECE(d) ((d) >> 29)            /* run descriptor -> current piece 0..6, 7 = empty queue (run length 0) */
 
 /* move / afterstate flags */
 #define TPL_FLAG_TOPOUT 1    /* drop row < 0: piece consumed, board and moves_used unchanged, state lost (:372-374) */
@@ -96,10 +110,12 @@ int tpl_unpack(const void *state, int64_t plane_stride, int n, uint16_t *rows, u
 /* Tetris.reset + load_warm_reset (:438-449) for the prescribed-config half: copy pool records into envs and
  * zero lines/moves/state/head.  idx i32[n] picks the config per env; idx == NULL draws
  * k = mulhi(philox(seed; env_base+i, episode[i], CONFIG).w0, K).  mode: TPL_RESET_*.  episode u32[n] (optional):
- * incremented for every env reset in mode TPL_RESET_DONE *before* the draw.  gen_count > 0 replaces the pool's
- * pieces by gen_count pieces of the counter-based 7-bag stream of (seed, env, episode). */
+ * incremented *before* the draw for every env reset in mode TPL_RESET_DONE, and in mode TPL_RESET_MASK when idx == NULL
+ * (a reset that draws its config starts a new episode; with explicit idx the caller owns the numbering).  tstep u32[n]
+ * (optional): the rollouts' per-episode action counter, zeroed for every env that is reset.  gen_count > 0 replaces the
+ * pool's pieces by gen_count pieces of the counter-based 7-bag stream of (seed, env, episode). */
 int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *pool, int K,
-                        const int32_t *idx, const uint8_t *mask, int mode, uint32_t *episode,
+                        const int32_t *idx, const uint8_t *mask, int mode, uint32_t *episode, uint32_t *tstep,
                         uint64_t seed, uint64_t env_base, int gen_count, void *stream);
 
 /* Tetris.move (:354-422) on every env: rot u8[n] (already reduced mod 4 by the caller; rot % n_rot is applied
@@ -123,8 +139,30 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
  * the three calls it replaces; results are identical to running them in sequence. */
 int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc,
                      int8_t *dlines, uint8_t *flags, int8_t *st, long long *stats,
-                     const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
+                     const void *pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count,
                      uint8_t *feats, uint8_t *aflags, float *feats_f32, int L, int M, void *stream);
+
+/* The distinct-placements form of tpl_afterstates / tpl_step_observe (see "data formats"): the same enumeration, but only the
+ * placements that differ are written -- 92 instead of 160 bytes per env on average, and no duplicate rows for a value net.
+ *   rows  u32[rows_capacity], 16-byte aligned, rows_capacity >= TPL_DISTINCT_CAPACITY(n) words
+ *   runs  u32[n] run descriptors; run_base is added to the offsets they report (not to the addresses written), so several
+ *         calls over sub-ranges of the envs can fill one array (tpl_env_step_observe_distinct does that)
+ *   cursor2 u32[2] device counters, zero before the first call: the call appends at cursor2[phase] (afterwards the number of
+ *         words used, gaps included) and clears cursor2[phase ^ 1]; alternate phase = 0, 1, 0, ... between consecutive calls
+ *         on the same stream and no memset is ever needed.  n <= 2^23 per call. */
+int tpl_afterstates_distinct(const void *state, int64_t plane_stride, int n, uint32_t *rows, int64_t rows_capacity,
+                             uint32_t *runs, uint32_t run_base, uint32_t *cursor2, int phase, int L, int M, void *stream);
+int tpl_step_observe_distinct(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc,
+                              int8_t *dlines, uint8_t *flags, int8_t *st, long long *stats,
+                              const void *pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base,
+                              int gen_count, uint32_t *rows, int64_t rows_capacity, uint32_t *runs, uint32_t run_base,
+                              uint32_t *cursor2, int phase, int L, int M, void *stream);
+/* distinct placements -> the compact 40-slot form feats u8[40][n][4] (byte 0 = rows cleared | flags << 3, TPL_FLAG_ALIAS on the
+ * slots that repeat an earlier one): what tpl_afterstates would have written.  Device pointers. */
+int tpl_expand_distinct(const uint32_t *rows, const uint32_t *runs, int n, uint8_t *feats, void *stream);
+/* Host tables of the numbering (any pointer may be NULL): count[7] = run length per piece; slot_of[7][34] = 40-slot index
+ * rot * 10 + loc of placement j (255 past the run's end); canon_of[7][40] = placement index that slot (rot, loc) aliases. */
+void tpl_distinct_tables(uint8_t *count, uint8_t *slot_of, uint8_t *canon_of);
 
 /* Counter-based 7-bag piece sequences (contract of RandomPieceGenerator.get_random_sequence, :95-102):
  * out u8[n][count]; episode u32[n] or NULL (= episode0 for all). */
@@ -174,10 +212,20 @@ int tpl_env_get_state(tpl_env *e, uint16_t *rows, uint8_t *cur, uint8_t *next, i
 int tpl_env_afterstates(tpl_env *e, uint8_t *feats, uint8_t *flags);
 /* one host-facing rollout step: H2D actions -> tpl_step_observe (move -> auto-reset of finished envs -> afterstates of
  * the new states, one kernel) -> D2H (dlines, flags, st, feats[, aflags]).  aflags == NULL selects the compact form
- * (feats byte 0 = rows cleared | flags << 3).  This is the call bench.py's e2e figure times.  feats == NULL (and
- * aflags == NULL) leaves the features on the device, see tpl_env_feats_ptr. */
+ * (feats byte 0 = rows cleared | flags << 3).  Large batches are pipelined over tpl_env_chunks(e) env chunks (the D2H of a
+ * chunk overlaps the kernel of the next).  feats == NULL (and aflags == NULL) leaves the features on the device, see
+ * tpl_env_feats_ptr. */
 int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
                          int8_t *st, uint8_t *feats, uint8_t *aflags);
+/* The same step in the distinct-placements form (tpl_step_observe_distinct): only the placements that differ cross PCIe
+ * (about 100 instead of 163 bytes per env-step).  rows: host u32[rows_capacity] with rows_capacity >=
+ * tpl_env_distinct_capacity(e); runs: host u32[n] run descriptors (offsets into rows).  The call works through the envs in
+ * tpl_env_chunks(e) chunks, each with its own region of rows, and overlaps the transfer of a chunk with the kernels of the
+ * next ones; *words_copied (optional) = rows words actually transferred. */
+int tpl_env_step_observe_distinct(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
+                                  int8_t *st, uint32_t *rows, int64_t rows_capacity, uint32_t *runs, int64_t *words_copied);
+int64_t tpl_env_distinct_capacity(tpl_env *e);
+int tpl_env_chunks(tpl_env *e);
 /* pinned (page-locked) host buffers so the copies inside the calls above are true async DMA */
 void *tpl_host_alloc(int64_t bytes);
 void tpl_host_free(void *p);

@@ -9,18 +9,23 @@ import os
 from ctypes import c_char_p, c_int, c_int64, c_longlong, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libtetris_piclim_sm100.so")
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libtetris_piclim_sm100.so")      # short in-tree path, see build.py
 
 P = c_void_p      # every array argument is passed as a raw address
+ABI_VERSION = 2   # TPL_ABI_VERSION of include/tetris_piclim.h
 
 # name -> (restype, argtypes); the trailing `stream` argument of the device API is listed explicitly
 DEVICE_API = {
     "pack": (c_int, [P, c_int64, c_int, c_int, P, P, c_int, P, P, P, P, P, P]),
     "unpack": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, P]),
-    "reset_from_pool": (c_int, [P, c_int64, c_int, P, c_int, P, P, c_int, P, c_uint64, c_uint64, c_int, P]),
+    "reset_from_pool": (c_int, [P, c_int64, c_int, P, c_int, P, P, c_int, P, P, c_uint64, c_uint64, c_int, P]),
     "step": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, c_int, c_int, P]),
     "afterstates": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P]),
-    "step_observe": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, c_uint64, c_uint64, c_int, P, P, P, c_int, c_int, P]),
+    "step_observe": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, P, c_uint64, c_uint64, c_int, P, P, P, c_int, c_int, P]),
+    "afterstates_distinct": (c_int, [P, c_int64, c_int, P, c_int64, P, c_uint32, P, c_int, c_int, c_int, P]),
+    "step_observe_distinct": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, P, c_uint64, c_uint64, c_int, P, c_int64, P, c_uint32,
+                                      P, c_int, c_int, c_int, P]),
+    "expand_distinct": (c_int, [P, P, c_int, P, P]),
     "gen_pieces": (c_int, [P, c_int, c_int, c_uint64, c_uint64, P, c_uint32, P]),
     "rollout_random": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int, c_int, c_int, P]),
     "rollout_greedy": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, P, c_uint64, c_uint64, c_int, c_int, c_int, P]),
@@ -37,6 +42,9 @@ HOST_API = {
     "env_get_state": (c_int, [c_void_p, P, P, P, P, P, P, P, P, P]),
     "env_afterstates": (c_int, [c_void_p, P, P]),
     "env_step_observe": (c_int, [c_void_p, P, P, P, P, P, P, P]),
+    "env_step_observe_distinct": (c_int, [c_void_p, P, P, P, P, P, P, c_int64, P, ctypes.POINTER(c_int64)]),
+    "env_distinct_capacity": (c_int64, [c_void_p]),
+    "env_chunks": (c_int, [c_void_p]),
     "env_feats_ptr": (c_void_p, [c_void_p]),
     "env_state_ptr": (c_void_p, [c_void_p, ctypes.POINTER(c_int64)]),
     "env_stream": (c_void_p, [c_void_p]),
@@ -48,6 +56,7 @@ MISC_API = {
     "abi_version": (c_int, []),
     "last_error": (c_char_p, []),
     "launch_count": (c_longlong, []),
+    "distinct_tables": (None, [P, P, P]),
 }
 
 ALL_SYMBOLS = ["tpl_" + k for k in list(DEVICE_API) + list(HOST_API) + list(MISC_API)]
@@ -74,7 +83,7 @@ def lib() -> ctypes.CDLL:
                 fn = getattr(L, "tpl_" + name)
                 fn.restype = res
                 fn.argtypes = args
-        if L.tpl_abi_version() != 1:
+        if L.tpl_abi_version() != ABI_VERSION:
             raise ImportError("libtetris_piclim_sm100.so: ABI version mismatch")
         _lib = L
     return _lib

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import distinct as _distinct
 from .configs import MAX_PIECES, ConfigPool
 
 RUNNING, WON, LOST = 0, 1, 2
@@ -62,6 +63,15 @@ class BatchedTetris:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _call(self, fn, what, *args):
+        """Run one C-ABI entry point with this env's device current (the launches inside use the CUDA *current* device;
+        an env on cuda:1 driven while cuda:0 is current would otherwise fail with an invalid resource handle)."""
+        if torch.cuda.current_device() == self.device.index:
+            _lib.check(fn(*args), what)
+        else:
+            with torch.cuda.device(self.device):
+                _lib.check(fn(*args), what)
+
     def _dev(self, x, dtype, shape=None) -> torch.Tensor:
         if isinstance(x, torch.Tensor):
             t = x.to(device=self.device, dtype=dtype)
@@ -107,8 +117,8 @@ class BatchedTetris:
             raise ValueError("piece ids must be 0..6")
         d_rows, d_p, d_np = self._dev(rows, torch.uint16), self._dev(pieces, torch.uint8), self._dev(npieces, torch.uint8)
         self.pool = torch.empty((K, 4, 4), dtype=torch.int32, device=self.device)
-        _lib.check(self._L.tpl_pack(_ptr(self.pool), 0, 1, K, _ptr(d_rows), _ptr(d_p), pieces.shape[1], _ptr(d_np),
-                                    None, None, None, None, self._stream()), "tpl_pack(pool)")
+        self._call(self._L.tpl_pack, "tpl_pack(pool)", _ptr(self.pool), 0, 1, K, _ptr(d_rows), _ptr(d_p), pieces.shape[1], _ptr(d_np),
+                                    None, None, None, None, self._stream())
         self.pool_size = K
 
     def reset(self, mask=None, idx=None, boards=None, pieces=None, npieces=None, done_only: bool = False) -> None:
@@ -117,7 +127,9 @@ class BatchedTetris:
         * ``boards``/``pieces`` given: install exactly these (uint16[N,20] bitrows or bool[N,20,10]; uint8[N,P]).
         * otherwise draw from the pool: ``idx`` int32[N] picks configs, else the counter RNG keyed by
           (seed, global env id, episode) does.  ``mask`` restricts the reset to some envs; ``done_only`` resets
-          exactly the envs whose episode has ended and bumps their episode counter (auto-reset)."""
+          exactly the envs whose episode has ended (auto-reset).  A reset that draws its configs (no ``idx``) from a
+          mask or with ``done_only`` starts a new episode: the per-env episode counter is bumped before the draw.
+          Every reset zeroes the reset envs' ``tstep`` (the rollouts' per-episode action counter)."""
         n = self.num_envs
         if boards is not None:
             if mask is not None or done_only:
@@ -132,11 +144,11 @@ class BatchedTetris:
         d_idx = self._dev(idx, torch.int32, (n,)) if idx is not None else None
         if mode == RESET_ALL:
             self.episode.zero_()
-        if mode != RESET_DONE:
-            (self.tstep.zero_() if d_mask is None else self.tstep.masked_fill_(d_mask.bool(), 0))
-        _lib.check(self._L.tpl_reset_from_pool(_ptr(self.state), self.stride, n, _ptr(self.pool), self.pool_size,
-                                               _ptr(d_idx), _ptr(d_mask), mode, _ptr(self.episode), self.seed,
-                                               self.env_base, self.gen_count, self._stream()), "tpl_reset_from_pool")
+        # the kernel zeroes tstep of every env it resets and bumps the episode counter of the envs whose config it draws
+        # itself (done_only, or mask without idx): `env.reset(mask=done)` gives each env a NEW config, not the old one again
+        self._call(self._L.tpl_reset_from_pool, "tpl_reset_from_pool", _ptr(self.state), self.stride, n, _ptr(self.pool), self.pool_size,
+                                               _ptr(d_idx), _ptr(d_mask), mode, _ptr(self.episode), _ptr(self.tstep), self.seed,
+                                               self.env_base, self.gen_count, self._stream())
 
     def load(self, boards, pieces, npieces=None, lines=None, moves=None, state=None, head=None) -> None:
         """Install explicit env states (boundary format).  Optional counters let tests resume mid-episode."""
@@ -154,11 +166,13 @@ class BatchedTetris:
         npn = np.asarray(npieces)
         if npn.max() > min(MAX_PIECES, p.shape[1]):
             raise ValueError("npieces exceeds the 42-piece queue or the pieces array")
+        if p.size and (int(p.max()) > 6 or int(p.min()) < 0):
+            raise ValueError("piece ids must be 0..6")
         d_p, d_np = self._dev(p, torch.uint8), self._dev(npn, torch.uint8, (n,))
         opt = lambda x, dt: self._dev(x, dt, (n,)) if x is not None else None   # noqa: E731
         d_lines, d_moves, d_st, d_head = opt(lines, torch.int32), opt(moves, torch.int32), opt(state, torch.int8), opt(head, torch.uint8)
-        _lib.check(self._L.tpl_pack(_ptr(self.state), self.stride, 0, n, _ptr(d_rows), _ptr(d_p), p.shape[1], _ptr(d_np),
-                                    _ptr(d_lines), _ptr(d_moves), _ptr(d_st), _ptr(d_head), self._stream()), "tpl_pack")
+        self._call(self._L.tpl_pack, "tpl_pack", _ptr(self.state), self.stride, 0, n, _ptr(d_rows), _ptr(d_p), p.shape[1], _ptr(d_np),
+                                    _ptr(d_lines), _ptr(d_moves), _ptr(d_st), _ptr(d_head), self._stream())
 
     # ------------------------------------------------------------------ move (C)
     def move(self, rot, loc) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -166,7 +180,8 @@ class BatchedTetris:
 
         ``rot`` may be any integers (reduced with Python's ``%`` like ``:61``); ``loc`` must be >= 0 (a negative
         location raises in the reference too) and is clamped to ``10 - width`` (``:364``).
-        Returns (rows cleared int8[N], flags uint8[N], state int8[N])."""
+        Returns (rows cleared int8[N], flags uint8[N], state int8[N]).  The three tensors are this object's output buffers:
+        valid until the next ``move`` / ``step_observe`` call, which overwrites them in place (``.clone()`` to keep)."""
         n = self.num_envs
         if isinstance(rot, torch.Tensor):
             # uint8 tensors go straight to the kernel (it applies rot & 3, and 256 % 4 == 0)
@@ -189,8 +204,8 @@ class BatchedTetris:
         dl = self._buf("dlines", (n,), torch.int8)
         fl = self._buf("mflags", (n,), torch.uint8)
         st = self._buf("mstate", (n,), torch.int8)
-        _lib.check(self._L.tpl_step(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
-                                    _ptr(self.stats) if self.count_stats else None, self.L, self.M, self._stream()), "tpl_step")
+        self._call(self._L.tpl_step, "tpl_step", _ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
+                                    _ptr(self.stats) if self.count_stats else None, self.L, self.M, self._stream())
         return dl, fl, st
 
     step = move
@@ -199,7 +214,8 @@ class BatchedTetris:
     def get_state(self, bool_boards: bool = False):
         """Batched ``Tetris.get_state`` (``game/tetris.py:435-436``):
         (boards uint16[N,20] or bool[N,20,10], current piece uint8[N], next piece uint8[N] (255 = none),
-        L - lines_cleared int32[N], M - moves_used int32[N], state int8[N])."""
+        L - lines_cleared int32[N], M - moves_used int32[N], state int8[N]).  Boards / pieces / state alias reused
+        output buffers (valid until the next ``get_state`` / ``fields`` call)."""
         f = self.fields()
         boards = f["rows"]
         if bool_boards:
@@ -207,14 +223,16 @@ class BatchedTetris:
         return boards, f["cur"], f["next"], self.L - f["lines"], self.M - f["moves"], f["state"]
 
     def fields(self, queue: bool = False) -> dict:
+        """Raw per-env fields (boundary format).  The tensors are reused output buffers: valid until the next ``fields`` /
+        ``get_state`` call."""
         n = self.num_envs
         rows = self._buf("rows", (n, 20), torch.uint16)
         cur, nxt = self._buf("cur", (n,), torch.uint8), self._buf("next", (n,), torch.uint8)
         lines, moves = self._buf("lines", (n,), torch.int32), self._buf("moves", (n,), torch.int32)
         st, head, npc = self._buf("state", (n,), torch.int8), self._buf("head", (n,), torch.uint8), self._buf("np", (n,), torch.uint8)
         q = self._buf("queue", (n, MAX_PIECES), torch.uint8) if queue else None
-        _lib.check(self._L.tpl_unpack(_ptr(self.state), self.stride, n, _ptr(rows), _ptr(cur), _ptr(nxt), _ptr(lines), _ptr(moves),
-                                      _ptr(st), _ptr(head), _ptr(npc), _ptr(q), self._stream()), "tpl_unpack")
+        self._call(self._L.tpl_unpack, "tpl_unpack", _ptr(self.state), self.stride, n, _ptr(rows), _ptr(cur), _ptr(nxt), _ptr(lines), _ptr(moves),
+                                      _ptr(st), _ptr(head), _ptr(npc), _ptr(q), self._stream())
         out = dict(rows=rows, cur=cur, next=nxt, lines=lines, moves=moves, state=st, head=head, npieces=npc)
         if queue:
             out["queue"] = q
@@ -231,15 +249,16 @@ class BatchedTetris:
 
         ``packed=True`` is the compact 160 B/env form: only ``feats`` is written and its byte 0 holds
         ``rows cleared | flags << 3``; returns (feats, None).  ``raw=True`` returns the slot-major buffers themselves
-        (uint8 [40, N, 4] and [40, N]) instead of the [N, 4, 10, ...] views."""
+        (uint8 [40, N, 4] and [40, N]) instead of the [N, 4, 10, ...] views.  All results alias this object's output buffers:
+        the next ``afterstates`` / ``step_observe`` call overwrites them in place."""
         n = self.num_envs
         if packed and f32:
             raise ValueError("the packed form has no float output")
         feats = self._buf("feats", (40, n, 4), torch.uint8) if (u8 or packed) else None
         flags = None if packed else self._buf("aflags", (40, n), torch.uint8)
         ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
-        _lib.check(self._L.tpl_afterstates(_ptr(self.state), self.stride, n, _ptr(feats), _ptr(flags), _ptr(ff), self.L, self.M,
-                                           self._stream()), "tpl_afterstates")
+        self._call(self._L.tpl_afterstates, "tpl_afterstates", _ptr(self.state), self.stride, n, _ptr(feats), _ptr(flags), _ptr(ff), self.L, self.M,
+                                           self._stream())
         if raw:
             return (feats, flags, ff) if f32 else (feats, flags)
         fv = feats.view(4, 10, n, 4).permute(2, 0, 1, 3) if feats is not None else None
@@ -251,7 +270,8 @@ class BatchedTetris:
         """move -> auto-reset of finished envs -> afterstates of the resulting state, in ONE kernel launch
         (``tpl_step_observe``): the rollout inner loop between two value-net calls.  ``rot``/``loc`` must be uint8
         CUDA tensors [N].  Returns (rows cleared, move flags, state after the move, feats, afterstate flags or None,
-        feats_f32 or None); ``feats`` is the raw slot-major uint8 [40, N, 4] buffer (compact form when ``packed``)."""
+        feats_f32 or None); ``feats`` is the raw slot-major uint8 [40, N, 4] buffer (compact form when ``packed``).
+        All results alias this object's output buffers (valid until the next call that writes them)."""
         n = self.num_envs
         if auto_reset:
             self._need_pool()
@@ -262,12 +282,59 @@ class BatchedTetris:
         feats = self._buf("feats", (40, n, 4), torch.uint8)
         aflags = None if packed else self._buf("aflags", (40, n), torch.uint8)
         ff = self._buf("feats_f32", (40 * n, 4), torch.float32) if f32 else None
-        _lib.check(self._L.tpl_step_observe(_ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
+        self._call(self._L.tpl_step_observe, "tpl_step_observe", _ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc), _ptr(dl), _ptr(fl), _ptr(st),
                                             _ptr(self.stats) if self.count_stats else None,
-                                            _ptr(self.pool) if auto_reset else None, self.pool_size, _ptr(self.episode), self.seed,
-                                            self.env_base, self.gen_count, _ptr(feats), _ptr(aflags), _ptr(ff), self.L, self.M,
-                                            self._stream()), "tpl_step_observe")
+                                            _ptr(self.pool) if auto_reset else None, self.pool_size, _ptr(self.episode), _ptr(self.tstep),
+                                            self.seed, self.env_base, self.gen_count, _ptr(feats), _ptr(aflags), _ptr(ff), self.L, self.M,
+                                            self._stream())
         return dl, fl, st, feats, aflags, ff
+
+    # ------------------------------------------------------------------ distinct-placements (alias-free) forms
+    def _distinct_bufs(self):
+        n = self.num_envs
+        rows = self._buf("drows", (_distinct.capacity(n),), torch.int32)
+        runs = self._buf("druns", (n,), torch.int32)
+        if "dcursor" not in self._out:
+            self._out["dcursor"] = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._phase = 0
+        phase = self._phase
+        self._phase ^= 1
+        return rows, runs, self._out["dcursor"], phase
+
+    def afterstates_distinct(self):
+        """The afterstates of every env in the distinct-placements form (``tpl_afterstates_distinct``): only the placements
+        that differ -- 9 / 17 / 34 per env instead of 40 aliased slots.  Returns (rows int32[capacity], runs int32[N],
+        used): ``rows`` holds one word per placement (byte 0 = rows cleared | flags << 3, holes, bumpiness, aggregate
+        height; view it as uint8 [-1, 4]), ``runs[i]`` = word offset of env i's run | piece << 29 (``distinct.run_offset`` /
+        ``run_piece`` / ``gather_index`` / ``expand``), ``used`` a 0-d device tensor = words of ``rows`` in use.
+        Valid until the next distinct call (the buffers are reused)."""
+        n = self.num_envs
+        rows, runs, cur, phase = self._distinct_bufs()
+        self._call(self._L.tpl_afterstates_distinct, "tpl_afterstates_distinct", _ptr(self.state), self.stride, n, _ptr(rows), rows.numel(),
+                   _ptr(runs), 0, _ptr(cur), phase, self.L, self.M, self._stream())
+        return rows, runs, cur[phase]
+
+    def step_observe_distinct(self, rot, loc, auto_reset: bool = True):
+        """``step_observe`` with the new states' afterstates in the distinct-placements form (``tpl_step_observe_distinct``).
+        Returns (rows cleared, move flags, state after the move, rows, runs, used) -- see ``afterstates_distinct``."""
+        n = self.num_envs
+        if auto_reset:
+            self._need_pool()
+        d_rot, d_loc = self._dev(rot, torch.uint8, (n,)), self._dev(loc, torch.uint8, (n,))
+        dl, fl, st = self._buf("dlines", (n,), torch.int8), self._buf("mflags", (n,), torch.uint8), self._buf("mstate", (n,), torch.int8)
+        rows, runs, cur, phase = self._distinct_bufs()
+        self._call(self._L.tpl_step_observe_distinct, "tpl_step_observe_distinct", _ptr(self.state), self.stride, n, _ptr(d_rot), _ptr(d_loc),
+                   _ptr(dl), _ptr(fl), _ptr(st), _ptr(self.stats) if self.count_stats else None,
+                   _ptr(self.pool) if auto_reset else None, self.pool_size, _ptr(self.episode), _ptr(self.tstep), self.seed, self.env_base,
+                   self.gen_count, _ptr(rows), rows.numel(), _ptr(runs), 0, _ptr(cur), phase, self.L, self.M, self._stream())
+        return dl, fl, st, rows, runs, cur[phase]
+
+    def expand_distinct(self, rows, runs):
+        """rows / runs of a distinct call -> the compact 40-slot form uint8 [40, N, 4] (``tpl_expand_distinct``)."""
+        n = self.num_envs
+        out = torch.empty((40, n, 4), dtype=torch.uint8, device=self.device)
+        self._call(self._L.tpl_expand_distinct, "tpl_expand_distinct", _ptr(rows), _ptr(runs), n, _ptr(out), self._stream())
+        return out
 
     # ------------------------------------------------------------------ fused rollouts
     def _need_pool(self):
@@ -278,24 +345,23 @@ class BatchedTetris:
         """``steps`` uniformly random moves per env with auto-reset; state stays in registers between moves.
         Episode statistics accumulate in ``self.stats`` (see STAT_NAMES)."""
         self._need_pool()
-        _lib.check(self._L.tpl_rollout_random(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
+        self._call(self._L.tpl_rollout_random, "tpl_rollout_random", _ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
                                               _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps), self.seed,
-                                              self.env_base, self.gen_count, self.L, self.M, self._stream()), "tpl_rollout_random")
+                                              self.env_base, self.gen_count, self.L, self.M, self._stream())
 
     def rollout_greedy(self, steps: int, weights: Sequence[int]) -> None:
         """``steps`` greedy moves per env: arg-max over the 40 afterstates of the integer linear value
         w0*dlines + w1*holes + w2*bumpiness + w3*agg_height (+ w4 on a win, + w5 on a loss / top-out)."""
         self._need_pool()
         w = (ctypes.c_int32 * 6)(*[int(x) for x in weights])
-        _lib.check(self._L.tpl_rollout_greedy(_ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
+        self._call(self._L.tpl_rollout_greedy, "tpl_rollout_greedy", _ptr(self.state), self.stride, self.num_envs, _ptr(self.pool), self.pool_size,
                                               _ptr(self.episode), _ptr(self.tstep), _ptr(self.stats), int(steps),
                                               ctypes.cast(w, ctypes.c_void_p), self.seed, self.env_base, self.gen_count,
-                                              self.L, self.M, self._stream()), "tpl_rollout_greedy")
+                                              self.L, self.M, self._stream())
 
     def gen_pieces(self, count: int, episode: int = 0) -> torch.Tensor:
         out = torch.empty((self.num_envs, count), dtype=torch.uint8, device=self.device)
-        _lib.check(self._L.tpl_gen_pieces(_ptr(out), self.num_envs, count, self.seed, self.env_base, None, episode, self._stream()),
-                   "tpl_gen_pieces")
+        self._call(self._L.tpl_gen_pieces, "tpl_gen_pieces", _ptr(out), self.num_envs, count, self.seed, self.env_base, None, episode, self._stream())
         return out
 
     def reduce_stats(self) -> dict:

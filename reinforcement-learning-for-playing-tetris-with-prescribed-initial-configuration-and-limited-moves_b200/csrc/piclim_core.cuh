@@ -43,11 +43,14 @@ enum : uint32_t { S_RUNNING = 0, S_WON = 1, S_LOST = 2 };
 //        once y * 0x01010101 + a.z
 //   a.w: cover mask: byte j = 0xFF for j < w (selects the new height), 0 for the columns the shape does not cover
 //   b.x: bo nibbles (4 bits per column, no sentinel) -- used by the column-aligned general path
-//   b.y: (1 << h) - 1      b.z: 20 - h (top-out iff y > 20 - h)      b.w: unused
+//   b.y: (1 << h) - 1      b.z: 20 - h (top-out iff y > 20 - h)
+//   b.w: the "distinct placements" (alias-free) numbering of this piece: bits 0-7 = index of placement (this rotation,
+//        column 0) in the piece's run of distinct placements (rotations r < n_rot, columns c <= 10 - w, rotation-major),
+//        0xFF when the rotation is an alias; bits 8-15 = length of the run (9 / 17 / 34)
 // ---------------------------------------------------------------------------------------------
 struct OrientEntry { uint32_t ax, ay, az, aw, bx, by, bz, bw; };
 
-constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool alias) {
+constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool alias, int rot_base = 0xFF, int run_len = 0) {
     int m[4] = {m0, m1, m2, m3};
     int h = 0, w = 0;
     for (int i = 0; i < 4; ++i) {
@@ -70,7 +73,7 @@ constexpr OrientEntry make_orient(int m0, int m1, int m2, int m3, int nrot, bool
     }
     return OrientEntry{cb | ((uint32_t)w << 16) | ((uint32_t)h << 20) | ((uint32_t)(nrot - 1) << 24) | (alias ? 1u << 28 : 0u),
                        bo, to4, cover,
-                       bon, (1u << h) - 1u, (uint32_t)(20 - h), 0u};
+                       bon, (1u << h) - 1u, (uint32_t)(20 - h), (uint32_t)(alias ? 0xFF : rot_base) | ((uint32_t)run_len << 8)};
 }
 
 // The afterstate enumeration reads the same facts once per rotation, already split into registers (no shift/mask work on
@@ -89,23 +92,23 @@ constexpr OrientWide make_wide(const OrientEntry &e) {
 struct OrientTable { OrientEntry e[28]; OrientWide w[28]; };
 
 // row masks top->bottom, bit j = shape column j, exactly the arrays at game/tetris.py:25-55
-#define TPL_O(a, b, c, d, n, al) make_orient(a, b, c, d, n, al)
+#define TPL_O(a, b, c, d, n, al, rb, len) make_orient(a, b, c, d, n, al, rb, len)
 constexpr OrientTable make_table() {
     OrientTable t{{
-    // I
-    TPL_O(0xF, 0, 0, 0, 2, false), TPL_O(1, 1, 1, 1, 2, false), TPL_O(0xF, 0, 0, 0, 2, true), TPL_O(1, 1, 1, 1, 2, true),
-    // L
-    TPL_O(4, 7, 0, 0, 4, false), TPL_O(3, 2, 2, 0, 4, false), TPL_O(7, 1, 0, 0, 4, false), TPL_O(1, 1, 3, 0, 4, false),
+    // I: 7 + 10 distinct placements
+    TPL_O(0xF, 0, 0, 0, 2, false, 0, 17), TPL_O(1, 1, 1, 1, 2, false, 7, 17), TPL_O(0xF, 0, 0, 0, 2, true, 0xFF, 17), TPL_O(1, 1, 1, 1, 2, true, 0xFF, 17),
+    // L: 8 + 9 + 8 + 9
+    TPL_O(4, 7, 0, 0, 4, false, 0, 34), TPL_O(3, 2, 2, 0, 4, false, 8, 34), TPL_O(7, 1, 0, 0, 4, false, 17, 34), TPL_O(1, 1, 3, 0, 4, false, 25, 34),
     // J
-    TPL_O(1, 7, 0, 0, 4, false), TPL_O(2, 2, 3, 0, 4, false), TPL_O(7, 4, 0, 0, 4, false), TPL_O(3, 1, 1, 0, 4, false),
+    TPL_O(1, 7, 0, 0, 4, false, 0, 34), TPL_O(2, 2, 3, 0, 4, false, 8, 34), TPL_O(7, 4, 0, 0, 4, false, 17, 34), TPL_O(3, 1, 1, 0, 4, false, 25, 34),
     // T
-    TPL_O(2, 7, 0, 0, 4, false), TPL_O(2, 3, 2, 0, 4, false), TPL_O(7, 2, 0, 0, 4, false), TPL_O(1, 3, 1, 0, 4, false),
-    // S
-    TPL_O(6, 3, 0, 0, 2, false), TPL_O(1, 3, 2, 0, 2, false), TPL_O(6, 3, 0, 0, 2, true), TPL_O(1, 3, 2, 0, 2, true),
+    TPL_O(2, 7, 0, 0, 4, false, 0, 34), TPL_O(2, 3, 2, 0, 4, false, 8, 34), TPL_O(7, 2, 0, 0, 4, false, 17, 34), TPL_O(1, 3, 1, 0, 4, false, 25, 34),
+    // S: 8 + 9
+    TPL_O(6, 3, 0, 0, 2, false, 0, 17), TPL_O(1, 3, 2, 0, 2, false, 8, 17), TPL_O(6, 3, 0, 0, 2, true, 0xFF, 17), TPL_O(1, 3, 2, 0, 2, true, 0xFF, 17),
     // Z
-    TPL_O(3, 6, 0, 0, 2, false), TPL_O(2, 3, 1, 0, 2, false), TPL_O(3, 6, 0, 0, 2, true), TPL_O(2, 3, 1, 0, 2, true),
-    // O
-    TPL_O(3, 3, 0, 0, 1, false), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true), TPL_O(3, 3, 0, 0, 1, true),
+    TPL_O(3, 6, 0, 0, 2, false, 0, 17), TPL_O(2, 3, 1, 0, 2, false, 8, 17), TPL_O(3, 6, 0, 0, 2, true, 0xFF, 17), TPL_O(2, 3, 1, 0, 2, true, 0xFF, 17),
+    // O: 9
+    TPL_O(3, 3, 0, 0, 1, false, 0, 9), TPL_O(3, 3, 0, 0, 1, true, 0xFF, 9), TPL_O(3, 3, 0, 0, 1, true, 0xFF, 9), TPL_O(3, 3, 0, 0, 1, true, 0xFF, 9),
     }, {}};
     for (int i = 0; i < 28; ++i) t.w[i] = make_wide(t.e[i]);
     return t;
@@ -121,6 +124,10 @@ __device__ __forceinline__ int orient_w(const uint4 &o) { return (o.x >> 16) & 7
 __device__ __forceinline__ int orient_h(const uint4 &o) { return (o.x >> 20) & 7; }
 __device__ __forceinline__ int orient_nrot(const uint4 &o) { return ((o.x >> 24) & 3) + 1; }
 __device__ __forceinline__ bool orient_alias(const uint4 &o) { return (o.x >> 28) & 1; }
+// `ob.w`: see b.w above
+__device__ __forceinline__ uint32_t orient_rot_base(const uint4 &ob) { return ob.w & 0xFFu; }
+__device__ __forceinline__ uint32_t orient_run_len(const uint4 &ob) { return (ob.w >> 8) & 0xFFu; }
+constexpr int DISTINCT_MAX = 34;     // most distinct placements any piece has (L, J, T)
 
 // ---------------------------------------------------------------------------------------------
 // env record in registers

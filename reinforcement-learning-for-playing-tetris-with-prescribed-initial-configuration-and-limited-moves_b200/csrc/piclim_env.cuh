@@ -4,6 +4,10 @@
 #pragma once
 #include "piclim_core.cuh"
 
+#ifndef TPL_PACKED_Y
+#define TPL_PACKED_Y 0              // tuning knob (see TPL_PAIR in afterstates_env_impl)
+#endif
+
 namespace tpl {
 
 // ---------------------------------------------------------------------------------------------
@@ -29,7 +33,7 @@ __device__ __forceinline__ void cols_to_rows(const uint32_t (&col)[COLS], uint16
 __device__ __forceinline__ void pack_queue(const uint8_t *pieces, int np, uint32_t (&q)[4]) {
     uint64_t lo = 0, hi = 0;
     for (int p = 0; p < np; ++p) {
-        const uint64_t v = pieces[p] & 7u;
+        const uint64_t v = pieces[p] > 6 ? 6u : pieces[p];       // ids are 0..6 (host entry points reject others); never index past the table
         const int bit = 3 * p;
         if (bit < 64) { lo |= v << bit; if (bit > 61) hi |= v >> (64 - bit); }
         else hi |= v << (bit - 64);
@@ -104,7 +108,14 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           uint32_t flN, uint32_t flT, int w,
                                           int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO4, uint32_t cover, uint32_t hm, int thr, uint32_t one,
-                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
+                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp,
+                                          int y_packed = 0) {
+    // Distinct-placements form: alias slots are not stored at all, so a column that no distinct placement of ANY piece reaches in
+    // this rotation is skipped outright -- rotation 0: column 9; rotation 2: columns 8 and 9 (the only two-wide shape there is O,
+    // whose rotation 2 is an alias); rotation 3: column 9 (the one-wide vertical I is an alias there).  36 of 40 slots are left.
+    if constexpr (Sink::RAGGED) {
+        if (C >= 8 && C > cmax_warp) return;
+    } else
     // No lane of this warp fits a shape at column C: only the clamp alias.  Without piece-sorted warps (UNIFORM) that is known
     // statically for column 9 of rotations 0 and 2, where the narrowest shape of any piece is two wide (cmax_warp = 8).
     if (UNIFORM ? (C > 6 && C > cmax_warp) : (C == 9 && cmax_warp < 9)) {
@@ -121,6 +132,9 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     // the value 1 from a kernel parameter -- opaque to ptxas, which would otherwise fuse each sum into an ALU-pipe
     // VIADDMNMX -- and the four-way max is VIMNMX3 + VIMNMX: 2 ALU-pipe instructions instead of 3.
     int y;
+#if TPL_PACKED_Y
+    y = y_packed;                                      // (hard drops of columns C and C + 1 taken together as s16x2, see TPL_PAIR)
+#else
     if (C <= 6) {
         const int t0 = (int)mad_fma_pipe((uint32_t)H[C], one, (uint32_t)nb0), t1 = (int)mad_fma_pipe((uint32_t)H[C + 1], one, (uint32_t)nb1);
         const int t2 = (int)mad_fma_pipe((uint32_t)H[C + 2], one, (uint32_t)nb2), t3 = (int)mad_fma_pipe((uint32_t)H[C + 3], one, (uint32_t)nb3);
@@ -128,6 +142,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     } else {
         y = max(max(H[C] + nb0, H[C + 1] + nb1), __viaddmax_s32(H[C + 3], nb3, H[C + 2] + nb2));
     }
+#endif
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
     // the piece lands on empty cells, so `column | piece image` is `column + piece image`: one IMAD per window column
@@ -139,7 +154,21 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
     uint32_t wnew = agg2 * 0x01000100u + K;
     wnew = b2 * 0x10000u + wnew;
-    if constexpr (Sink::PACKED) {
+    if constexpr (Sink::RAGGED) {
+        // distinct placements only: no alias bookkeeping (no carried word / pend), a column the shape does not fit is simply not
+        // stored; lanes whose rotation is an alias store to a dummy row (begin_rotation_ragged) and their pmask is dropped
+        const bool pnew = full != 0u;
+        if (C <= 6) {                                  // every width fits (w <= 4)
+            if (!pnew) sink.template put_col<C>(wnew);
+            if (top) sink.template put_col<C>(U);
+            if (pnew) pmask |= 1u << C;
+        } else {
+            const bool fits = C + w <= COLS;
+            if (fits && !pnew) sink.template put_col<C>(wnew);
+            if (fits && top) sink.template put_col<C>(U);
+            if (fits && pnew) pmask |= 1u << C;
+        }
+    } else if constexpr (Sink::PACKED) {
         // compact form: the flags ride in byte 0 (K and U already carry flN << 3 / flT << 3 for this rotation)
         if (C <= 5) {
             // Columns every width fits and no later column aliases: no select at all.  The no-clear word is stored unless
@@ -199,11 +228,15 @@ __device__ __forceinline__ void resolve_slot(const uint32_t (&cols)[COLS], const
     const uint32_t word = (uint32_t)m.k | (f3 << 8);
     const uint32_t fl = m.topout ? F_TOPOUT :
                         m.k == 0 ? cx.fl_noclear : (((int)cx.lines + m.k >= L) ? F_WIN : cx.fl_noclear);   // :389-391, :415-422
-    const int nrot = orient_nrot(o), w = orient_w(o);
-    const int cend = (c == COLS - w) ? COLS - 1 : c;
-    for (int r2 = r; r2 < 4; r2 += nrot)
-        for (int c2 = c; c2 <= cend; ++c2)
-            sink.put(r2 * 10 + c2, word, fl | ((r2 != r || c2 != c) ? F_ALIAS : 0u));
+    if constexpr (Sink::RAGGED) {
+        sink.put_canon((int)orient_rot_base(ob) + c, word | (fl << 3));       // deferred slots are canonical placements
+    } else {
+        const int nrot = orient_nrot(o), w = orient_w(o);
+        const int cend = (c == COLS - w) ? COLS - 1 : c;
+        for (int r2 = r; r2 < 4; r2 += nrot)
+            for (int c2 = c; c2 <= cend; ++c2)
+                sink.put(r2 * 10 + c2, word, fl | ((r2 != r || c2 != c) ? F_ALIAS : 0u));
+    }
 }
 
 // UNIFORM = true is the variant for warps whose lanes were sorted by piece (afterstates_sorted_kernel): every lane of
@@ -219,8 +252,10 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
                                                      int r_begin = 0, int r_end = 4, PendingCtx *defer = nullptr, uint32_t one = 1u) {
     if (defer) defer->mask = 0ull;
     const bool nopiece = e.head >= e.npieces;
+    static_assert(!(UNIFORM && Sink::RAGGED), "the distinct-placements form is not built for piece-sorted warps");
     if (!UNIFORM && nopiece) {
-        for (int s = r_begin * 10; s < r_end * 10; ++s) sink.put(s, 0u, F_NOPIECE);
+        if constexpr (!Sink::RAGGED)                    // (distinct-placements form: an env without a piece has an empty run)
+            for (int s = r_begin * 10; s < r_end * 10; ++s) sink.put(s, 0u, F_NOPIECE);
         return;
     }
     // a lane without a piece walks through as an O piece (its stores are overwritten at the end)
@@ -236,6 +271,11 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     for (int k = 0; k < COLS; ++k) { col[k] = e.col[k]; H[k] = col_height(col[k]); cells += __popc(col[k]); }
 #pragma unroll
     for (int k = COLS; k < 14; ++k) { col[k] = COL_FULL; H[k] = 0; }
+#if TPL_PACKED_Y
+    uint32_t HP[13];                                 // HP[c] = H[c] | H[c + 1] << 16
+#pragma unroll
+    for (int k = 0; k < 13; ++k) HP[k] = (uint32_t)H[k] | ((uint32_t)H[k + 1] << 16);
+#endif
     const uint32_t HB0 = H[0] | (H[1] << 8) | (H[2] << 16) | (H[3] << 24);
     const uint32_t HB1 = H[4] | (H[5] << 8) | (H[6] << 16) | (H[7] << 24);
     const uint32_t HB2 = H[8] | (H[9] << 8);
@@ -277,6 +317,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const int w = orient_w(o);
         // widest reach of any piece in this rotation: the only one-wide shape is the vertical I, rotations 1 and 3 (game/tetris.py:25-55)
         int cmax_warp = (r & 1) ? 9 : 8;
+        if constexpr (Sink::RAGGED) cmax_warp = (r == 1) ? 9 : (r == 2) ? 7 : 8;        // see slot_fast
         if constexpr (UNIFORM) cmax_warp = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(COLS - w));
         const uint4 *wide = tab + TAB_COMPACT4 + (piece * 4 + r) * 3;              // the same facts, one register each
         const uint4 wn = wide[0], wc = wide[1], wm = wide[2];
@@ -287,10 +328,23 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         const uint32_t flN = fl_noclear | afl, flT = F_TOPOUT | afl;
         const uint32_t Kr = Sink::PACKED ? K + (flN << 3) : K, Ur = Sink::PACKED ? (U | (flT << 3)) : U;
         uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
-        if constexpr (Sink::PACKED) sink.begin_rotation(r);
-#define TPL_SLOT(C) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
-                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
-        TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
+        if constexpr (Sink::RAGGED) sink.begin_rotation_ragged(canon, orient_rot_base(tab[(piece * 4 + r) * 2 + 1]));
+        else if constexpr (Sink::PACKED) sink.begin_rotation(r);
+#define TPL_SLOT(C, Y) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
+                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp, Y);
+#if TPL_PACKED_Y
+        // Two adjacent columns share one packed hard drop: halves (H[c], H[c+1]) + (nb_j, nb_j) through four s16x2 add-max
+        // instructions (VIADDMNMX.S16x2) give y(c) | y(c + 1) << 16 -- 2 instructions per slot instead of 4 adds + 2 max.
+        const uint32_t NB0 = ((uint32_t)nb0 & 0xFFFFu) * 0x10001u, NB1 = ((uint32_t)nb1 & 0xFFFFu) * 0x10001u,
+                       NB2 = ((uint32_t)nb2 & 0xFFFFu) * 0x10001u, NB3 = ((uint32_t)nb3 & 0xFFFFu) * 0x10001u;
+#define TPL_PAIR(C) { uint32_t y2 = __viaddmax_s16x2(HP[C], NB0, 0x80008000u); y2 = __viaddmax_s16x2(HP[C + 1], NB1, y2); \
+                      y2 = __viaddmax_s16x2(HP[C + 2], NB2, y2); y2 = __viaddmax_s16x2(HP[C + 3], NB3, y2); \
+                      TPL_SLOT(C, (int)(y2 & 0xFFFFu)) TPL_SLOT(C + 1, (int)(y2 >> 16)) }      /* y >= 0 wherever the shape fits */
+        TPL_PAIR(0) TPL_PAIR(2) TPL_PAIR(4) TPL_PAIR(6) TPL_PAIR(8)
+#undef TPL_PAIR
+#else
+        TPL_SLOT(0, 0) TPL_SLOT(1, 0) TPL_SLOT(2, 0) TPL_SLOT(3, 0) TPL_SLOT(4, 0) TPL_SLOT(5, 0) TPL_SLOT(6, 0) TPL_SLOT(7, 0) TPL_SLOT(8, 0) TPL_SLOT(9, 0)
+#endif
 #undef TPL_SLOT
         if (canon) pending |= (unsigned long long)pmask << (10 * r);
         if constexpr (UNIFORM) notstored |= (unsigned long long)nsmask << (10 * r);
@@ -374,7 +428,7 @@ __device__ __forceinline__ int greedy_value(int w0, int w1, int w2, int w3, int 
 
 template <bool W16>
 struct GreedySinkT {
-    static constexpr bool PACKED = false;
+    static constexpr bool PACKED = false, RAGGED = false;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
@@ -385,7 +439,7 @@ struct GreedySinkT {
 
 // records the first put only: resolve_slot stores the canonical slot first, its aliases (equal value, higher index) after
 struct FirstPutSink {
-    static constexpr bool PACKED = false;
+    static constexpr bool PACKED = false, RAGGED = false;
     uint32_t word, fl; bool got;
     __device__ __forceinline__ void put(int, uint32_t w, uint32_t f) { if (!got) { word = w; fl = f; got = true; } }
 };

@@ -12,6 +12,9 @@
 namespace tpl { int fail(int code, const char *fmt, ...); }
 using tpl::fail;
 
+#ifndef TPL_MAX_CHUNKS
+#define TPL_MAX_CHUNKS 8
+#endif
 struct tpl_env {
     int n = 0, L = 0, M = 0, device = 0;
     uint64_t seed = 0, env_base = 0;
@@ -26,6 +29,15 @@ struct tpl_env {
     uint16_t *d_rows = nullptr; uint8_t *d_cur = nullptr, *d_next = nullptr, *d_head = nullptr, *d_np = nullptr, *d_queue = nullptr;
     int32_t *d_lines = nullptr, *d_moves = nullptr;
     void *d_scratch = nullptr; size_t scratch_bytes = 0;            // uploads for load / set_pool / reset
+    // pipelined rollout step (tpl_env_step_observe*): the envs are cut into chunks; the kernel of chunk c + 1 runs on `stream`
+    // while the results of chunk c travel to the host on `copy_stream`
+    int nchunks = 1; int chunk_envs = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[TPL_MAX_CHUNKS] = {};
+    uint32_t *d_tstep = nullptr;
+    uint32_t *d_drows = nullptr, *d_runs = nullptr, *d_cursor2 = nullptr;   // distinct-placements form: rows regions per chunk, descriptors, 2 counters per chunk
+    uint32_t *h_cursor = nullptr;                                    // pinned: words each chunk produced
+    int phase = 0;
 };
 
 #define CU(call)                                                                                     \
@@ -82,11 +94,21 @@ int tpl_env_create(tpl_env **out, int n, int L, int M, int device, uint64_t seed
     if (!e) return fail(TPL_ENOMEM, "tpl_env_create: out of host memory");
     e->n = n; e->L = L; e->M = M; e->device = device; e->seed = seed; e->env_base = env_base;
     e->stride = ((int64_t)n + 31) / 32 * 32;
+    // chunks of the pipelined step: multiples of 32 envs (a chunk starts on a tile boundary of the state planes), at least
+    // 64 Ki envs each so that a chunk still fills the GPU
+    e->nchunks = n / 65536; if (e->nchunks < 1) e->nchunks = 1; if (e->nchunks > TPL_MAX_CHUNKS) e->nchunks = TPL_MAX_CHUNKS;
+    if (const char *v = getenv("TPL_ENV_CHUNKS")) { int c = atoi(v); if (c >= 1 && c <= TPL_MAX_CHUNKS) e->nchunks = c; }
+    e->chunk_envs = (int)((((int64_t)n + e->nchunks - 1) / e->nchunks + 31) / 32 * 32);
+    e->nchunks = (n + e->chunk_envs - 1) / e->chunk_envs;
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    for (int c = 0; c < e->nchunks && err == cudaSuccess; ++c) err = cudaEventCreateWithFlags(&e->ev_done[c], cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaMalloc(&e->state, (size_t)e->stride * 64);
     if (err == cudaSuccess) err = cudaMemsetAsync(e->state, 0, (size_t)e->stride * 64, e->stream);
     if (err == cudaSuccess) err = cudaMalloc((void **)&e->episode, (size_t)n * 4);
     if (err == cudaSuccess) err = cudaMemsetAsync(e->episode, 0, (size_t)n * 4, e->stream);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_tstep, (size_t)n * 4);
+    if (err == cudaSuccess) err = cudaMemsetAsync(e->d_tstep, 0, (size_t)n * 4, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     if (err != cudaSuccess) { int r = fail((int)err, "tpl_env_create: %s", cudaGetErrorString(err)); tpl_env_destroy(e); return r; }
     *out = e;
@@ -97,7 +119,10 @@ void tpl_env_destroy(tpl_env *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *ptrs[] = {e->state, e->pool, e->episode, e->d_rot, e->d_loc, e->d_flags, e->d_dlines, e->d_st, e->d_feats, e->d_aflags,
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    for (int c = 0; c < TPL_MAX_CHUNKS; ++c) if (e->ev_done[c]) cudaEventDestroy(e->ev_done[c]);
+    if (e->h_cursor) cudaFreeHost(e->h_cursor);
+    void *ptrs[] = {e->d_tstep, e->d_drows, e->d_runs, e->d_cursor2, e->state, e->pool, e->episode, e->d_rot, e->d_loc, e->d_flags, e->d_dlines, e->d_st, e->d_feats, e->d_aflags,
                     e->d_rows, e->d_cur, e->d_next, e->d_head, e->d_np, e->d_queue, e->d_lines, e->d_moves, e->d_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -119,7 +144,12 @@ static int upload_pack(tpl_env *e, void *out, int64_t stride, int aos, int m, co
                        int pstride, const uint8_t *npieces, const int32_t *lines, const int32_t *moves, const int8_t *st,
                        const uint8_t *head) {
     if (!rows || !pieces || !npieces || pstride <= 0) return fail(TPL_EINVAL, "upload: rows/pieces/npieces required");
-    for (int i = 0; i < m; ++i) if (npieces[i] > TPL_MAX_PIECES) return fail(TPL_ERANGE, "config %d has %d pieces (> 42)", i, npieces[i]);
+    for (int i = 0; i < m; ++i) {
+        if (npieces[i] > TPL_MAX_PIECES || npieces[i] > pstride)
+            return fail(TPL_ERANGE, "config %d has %d pieces (> min(42, pieces_stride = %d))", i, npieces[i], pstride);
+        for (int q = 0; q < npieces[i]; ++q)
+            if (pieces[(size_t)i * pstride + q] > 6) return fail(TPL_ERANGE, "config %d: piece id %d at position %d (ids are 0..6)", i, pieces[(size_t)i * pstride + q], q);
+    }
     const size_t b_rows = al16((size_t)m * 40), b_p = al16((size_t)m * pstride), b_np = al16((size_t)m), b_i32 = al16((size_t)m * 4);
     RC(ensure_scratch(e, b_rows + b_p + 3 * b_np + 2 * b_i32));
     char *base = (char *)e->d_scratch; size_t off = 0;
@@ -171,7 +201,7 @@ int tpl_env_reset(tpl_env *e, const int32_t *idx, const uint8_t *mask, int mode,
     if (mask) CU(cudaMemcpyAsync(d_mask, mask, (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
     if (mode == TPL_RESET_ALL) CU(cudaMemsetAsync(e->episode, 0, (size_t)e->n * 4, e->stream));
     RC(tpl_reset_from_pool(e->state, e->stride, e->n, e->pool, e->K, idx ? d_idx : nullptr, mask ? d_mask : nullptr, mode,
-                           e->episode, e->seed, e->env_base, gen_count, e->stream));
+                           e->episode, e->d_tstep, e->seed, e->env_base, gen_count, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -247,30 +277,101 @@ int tpl_env_afterstates(tpl_env *e, uint8_t *feats, uint8_t *flags) {
     return 0;
 }
 
+// One rollout step through host buffers, pipelined over env chunks: on `stream`, for each chunk, H2D of its actions and the
+// fused kernel; on `copy_stream`, as soon as a chunk's kernel is done, D2H of its results -- so the transfer of chunk c
+// overlaps the kernel (and the action upload) of chunk c + 1, and the PCIe link never waits for the whole batch.
+// 40-slot forms: a chunk's kernel writes chunk-local slot-major arrays [40][nc]; one strided 2-D copy per array puts them at
+// the chunk's columns of the caller's [40][n] host arrays.
 int tpl_env_step_observe(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags, int8_t *st,
                          uint8_t *feats, uint8_t *aflags) {
     if (!e || !rot || !loc) return fail(TPL_EINVAL, "tpl_env_step_observe: null argument");
     if (!e->pool) return fail(TPL_EINVAL, "tpl_env_step_observe: no config pool (call tpl_env_set_pool first)");
+    if (!feats && aflags) return fail(TPL_EINVAL, "tpl_env_step_observe: aflags without feats");
     CU(cudaSetDevice(e->device));
     RC(ensure_move_bufs(e));
     const size_t n = (size_t)e->n;
-    CU(cudaMemcpyAsync(e->d_rot, rot, n, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->d_loc, loc, n, cudaMemcpyHostToDevice, e->stream));
-    if (!feats && aflags) return fail(TPL_EINVAL, "tpl_env_step_observe: aflags without feats");
     RC(ensure_feats(e, n * 160));
     if (aflags) RC(ensure((void **)&e->d_aflags, n * 40));
-    RC(tpl_step_observe(e->state, e->stride, e->n, e->d_rot, e->d_loc, e->d_dlines, e->d_flags, e->d_st, nullptr, e->pool, e->K,
-                        e->episode, e->seed, e->env_base, 0, e->d_feats, aflags ? e->d_aflags : nullptr, nullptr, e->L, e->M, e->stream));
-    if (dlines) CU(cudaMemcpyAsync(dlines, e->d_dlines, n, cudaMemcpyDeviceToHost, e->stream));
-    if (flags) CU(cudaMemcpyAsync(flags, e->d_flags, n, cudaMemcpyDeviceToHost, e->stream));
-    if (st) CU(cudaMemcpyAsync(st, e->d_st, n, cudaMemcpyDeviceToHost, e->stream));
-    // feats == NULL: the 40-slot features stay in HBM (compact form, tpl_env_feats_ptr) for a policy that runs on the GPU;
-    // only the move's results travel back
-    if (feats) CU(cudaMemcpyAsync(feats, e->d_feats, n * 160, cudaMemcpyDeviceToHost, e->stream));
-    if (aflags) CU(cudaMemcpyAsync(aflags, e->d_aflags, n * 40, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    // (features left on the device: one chunk, so that tpl_env_feats_ptr is one [40][n] array -- nothing big to overlap anyway)
+    const int nchunks = feats ? e->nchunks : 1;
+    const size_t chunk_envs = feats ? (size_t)e->chunk_envs : n;
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t c0 = (size_t)c * chunk_envs, nc = (c0 + chunk_envs <= n) ? chunk_envs : n - c0;
+        CU(cudaMemcpyAsync(e->d_rot + c0, rot + c0, nc, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_loc + c0, loc + c0, nc, cudaMemcpyHostToDevice, e->stream));
+        uint8_t *cf = e->d_feats + c0 * 160, *ca = aflags ? e->d_aflags + c0 * 40 : nullptr;
+        RC(tpl_step_observe((uint4 *)e->state + c0, e->stride, (int)nc, e->d_rot + c0, e->d_loc + c0, e->d_dlines + c0, e->d_flags + c0,
+                            e->d_st + c0, nullptr, e->pool, e->K, e->episode + c0, e->d_tstep + c0, e->seed, e->env_base + c0, 0, cf, ca,
+                            nullptr, e->L, e->M, e->stream));
+        CU(cudaEventRecord(e->ev_done[c], e->stream));
+        CU(cudaStreamWaitEvent(e->copy_stream, e->ev_done[c], 0));
+        if (dlines) CU(cudaMemcpyAsync(dlines + c0, e->d_dlines + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (flags) CU(cudaMemcpyAsync(flags + c0, e->d_flags + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (st) CU(cudaMemcpyAsync(st + c0, e->d_st + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+        // feats == NULL: the 40-slot features stay in HBM (compact form, tpl_env_feats_ptr) for a policy that runs on the GPU;
+        // only the move's results travel back
+        if (feats) CU(cudaMemcpy2DAsync(feats + c0 * 4, n * 4, cf, nc * 4, nc * 4, 40, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (aflags) CU(cudaMemcpy2DAsync(aflags + c0, n, ca, nc, nc, 40, cudaMemcpyDeviceToHost, e->copy_stream));
+    }
+    CU(cudaStreamSynchronize(e->copy_stream));
     return 0;
 }
+
+// The same step in the distinct-placements form (tpl_step_observe_distinct): only the placements that differ cross PCIe.
+// rows (host, >= TPL_DISTINCT_CAPACITY(n) + 4 * chunks words): chunk c writes into its own region of the array; runs (host,
+// u32[n]) says where each env's run starts in it.  How many words a chunk produced is only known after its kernel, so the
+// host reads the chunk's counter (4 bytes, behind the kernel on `stream`) and then queues exactly that many words on
+// `copy_stream` -- while the later chunks' kernels are already running.  *words_copied = total rows words transferred.
+int tpl_env_step_observe_distinct(tpl_env *e, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags, int8_t *st,
+                                  uint32_t *rows, int64_t rows_capacity, uint32_t *runs, int64_t *words_copied) {
+    if (!e || !rot || !loc || !rows || !runs) return fail(TPL_EINVAL, "tpl_env_step_observe_distinct: null argument");
+    if (!e->pool) return fail(TPL_EINVAL, "tpl_env_step_observe_distinct: no config pool (call tpl_env_set_pool first)");
+    const int64_t region = TPL_DISTINCT_CAPACITY(e->chunk_envs);                 // words per chunk region (device and host)
+    if (rows_capacity < region * e->nchunks)
+        return fail(TPL_ERANGE, "tpl_env_step_observe_distinct: rows_capacity %lld < %lld words (tpl_env_distinct_capacity)",
+                    (long long)rows_capacity, (long long)(region * e->nchunks));
+    CU(cudaSetDevice(e->device));
+    RC(ensure_move_bufs(e));
+    const size_t n = (size_t)e->n;
+    RC(ensure((void **)&e->d_drows, (size_t)region * e->nchunks * 4));
+    RC(ensure((void **)&e->d_runs, n * 4));
+    if (!e->d_cursor2) {
+        RC(ensure((void **)&e->d_cursor2, 2 * TPL_MAX_CHUNKS * 4));
+        CU(cudaMemsetAsync(e->d_cursor2, 0, 2 * TPL_MAX_CHUNKS * 4, e->stream));
+        CU(cudaHostAlloc((void **)&e->h_cursor, TPL_MAX_CHUNKS * 4, cudaHostAllocDefault));
+    }
+    const int phase = e->phase; e->phase ^= 1;
+    for (int c = 0; c < e->nchunks; ++c) {
+        const size_t c0 = (size_t)c * e->chunk_envs, nc = (c0 + e->chunk_envs <= n) ? (size_t)e->chunk_envs : n - c0;
+        CU(cudaMemcpyAsync(e->d_rot + c0, rot + c0, nc, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_loc + c0, loc + c0, nc, cudaMemcpyHostToDevice, e->stream));
+        RC(tpl_step_observe_distinct((uint4 *)e->state + c0, e->stride, (int)nc, e->d_rot + c0, e->d_loc + c0, e->d_dlines + c0,
+                                     e->d_flags + c0, e->d_st + c0, nullptr, e->pool, e->K, e->episode + c0, e->d_tstep + c0, e->seed,
+                                     e->env_base + c0, 0, e->d_drows + region * c, region, e->d_runs + c0, (uint32_t)(region * c),
+                                     e->d_cursor2 + 2 * c, phase, e->L, e->M, e->stream));
+        CU(cudaMemcpyAsync(e->h_cursor + c, e->d_cursor2 + 2 * c + phase, 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->ev_done[c], e->stream));
+    }
+    int64_t total = 0;
+    for (int c = 0; c < e->nchunks; ++c) {
+        const size_t c0 = (size_t)c * e->chunk_envs, nc = (c0 + e->chunk_envs <= n) ? (size_t)e->chunk_envs : n - c0;
+        CU(cudaEventSynchronize(e->ev_done[c]));
+        const size_t words = e->h_cursor[c];
+        if ((int64_t)words > region) return fail(TPL_ERANGE, "tpl_env_step_observe_distinct: chunk %d produced %zu words > region", c, words);
+        total += (int64_t)words;
+        CU(cudaMemcpyAsync(rows + region * c, e->d_drows + region * c, words * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+        CU(cudaMemcpyAsync(runs + c0, e->d_runs + c0, nc * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (dlines) CU(cudaMemcpyAsync(dlines + c0, e->d_dlines + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (flags) CU(cudaMemcpyAsync(flags + c0, e->d_flags + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+        if (st) CU(cudaMemcpyAsync(st + c0, e->d_st + c0, nc, cudaMemcpyDeviceToHost, e->copy_stream));
+    }
+    CU(cudaStreamSynchronize(e->copy_stream));
+    if (words_copied) *words_copied = total;
+    return 0;
+}
+
+int64_t tpl_env_distinct_capacity(tpl_env *e) { return e ? TPL_DISTINCT_CAPACITY(e->chunk_envs) * e->nchunks : 0; }
+int tpl_env_chunks(tpl_env *e) { return e ? e->nchunks : 0; }
 
 void *tpl_env_feats_ptr(tpl_env *e) { return e ? (void *)e->d_feats : nullptr; }
 

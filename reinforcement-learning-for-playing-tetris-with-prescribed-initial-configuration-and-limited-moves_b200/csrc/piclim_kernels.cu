@@ -51,7 +51,7 @@ pack_kernel(uint4 *out, int64_t stride, int aos, int n, const uint16_t *__restri
     if (i >= n) return;
     Env e;
     rows_to_cols(rows + i * ROWS, e.col);
-    const int np = min((int)npieces[i], TPL_MAX_PIECES);
+    const int np = min(min((int)npieces[i], TPL_MAX_PIECES), pstride);
     pack_queue(pieces + i * pstride, np, e.q);
     e.lines = lines ? (uint32_t)lines[i] : 0u;
     e.moves = moves ? (uint32_t)moves[i] : 0u;
@@ -85,7 +85,7 @@ unpack_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint16_t *row
 // =================================================================================================
 __global__ void __launch_bounds__(THREADS)
 reset_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, int K, const int32_t *__restrict__ idx,
-             const uint8_t *__restrict__ mask, int mode, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count) {
+             const uint8_t *__restrict__ mask, int mode, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count) {
     const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
     if (i >= n) return;
     if (mode == TPL_RESET_MASK && !mask[i]) return;
@@ -94,9 +94,14 @@ reset_kernel(uint4 *st, int64_t stride, int n, const uint4 *__restrict__ pool, i
         const uint4 d = st[3 * stride + i];
         const uint32_t state = d.w & 0xFFu, head = (d.w >> 8) & 0xFFu, np = (d.w >> 16) & 0xFFu;
         if (state == S_RUNNING && head < np) return;
+    }
+    // a masked or auto reset WITHOUT explicit indices starts a new episode: the counter is bumped before the draw, so the env
+    // does not get the config (and the action stream) of the episode it just finished again
+    if (mode == TPL_RESET_DONE || (mode == TPL_RESET_MASK && !idx)) {
         ep += 1;
         if (episode) episode[i] = ep;
     }
+    if (tstep) tstep[i] = 0u;                           // every reset path restarts the rollouts' per-episode action stream
     uint32_t k;
     if (idx) { const int32_t v = idx[i]; k = (uint32_t)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
     else k = config_index(seed, env_base + (uint64_t)i, ep, K);
@@ -175,7 +180,7 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
 // one slot row is a 32-bit add on its low word -- one instruction instead of the IADD3 + IMAD.X pair of a 64-bit add.
 template <int MODE, bool P32 = false>
 struct GlobalSink {
-    static constexpr bool PACKED = (MODE == 0);
+    static constexpr bool PACKED = (MODE == 0), RAGGED = false;
     uint32_t *words; uint8_t *flags; float4 *ff;      // already offset by the env index
     uint32_t n;
     uint32_t one;                                     // the value 1 from a kernel parameter, i.e. opaque to ptxas (see next_col)
@@ -212,6 +217,52 @@ struct GlobalSink {
     }
 };
 
+// ---- distinct-placements ("ragged") output form (MODE 4) -------------------------------------------------------------------
+// Only the placements that differ are written: rotations r < n_rot (game/tetris.py:61) and columns c <= 10 - w (:364), in
+// rotation-major order -- 9 (O), 17 (I, S, Z) or 34 (L, J, T) words per env, 23.1 on average instead of 40.  The runs of a
+// 32-env tile are packed back to back: each lane writes its words into the warp's staging area in shared memory at the
+// exclusive prefix of the run lengths (a 32-bit shared-memory address + an immediate per column: no pointer arithmetic per
+// slot), the warp reserves `total` words of the output array with ONE atomicAdd on the cursor (issued before the
+// enumeration, consumed after it), and the tile leaves the SM as contiguous 16-byte stores.  Where an env's run starts is
+// reported per env (`runs[i] = word offset | piece << 29`), so the order of the tiles in the array does not matter.
+constexpr int RAG_STAGE_WORDS = DISTINCT_MAX * 32 + 16;      // + a 10-word dummy row for the lanes whose rotation is an alias
+constexpr int RAG_DUMMY_WORD = DISTINCT_MAX * 32;
+constexpr int RAG_SMEM_BYTES = RAG_STAGE_WORDS * 4 * (THREADS / 32);
+
+struct RaggedStageSink {
+    static constexpr bool PACKED = true, RAGGED = true;
+    uint32_t run_saddr;        // shared-space byte address of this env's run in the staging area
+    uint32_t dummy_saddr;      // ... of the warp's dummy row
+    uint32_t prow;             // ... of placement (current rotation, column 0)
+    __device__ __forceinline__ void begin_rotation_ragged(bool canon, uint32_t rot_base) {
+        prow = canon ? run_saddr + rot_base * 4u : dummy_saddr;
+    }
+    template <int C> __device__ __forceinline__ void put_col(uint32_t w) {
+#ifdef __CUDA_ARCH__
+        asm volatile("st.shared.b32 [%0+%1], %2;" :: "r"(prow), "n"(C * 4), "r"(w) : "memory");
+#endif
+    }
+    __device__ __forceinline__ void put_canon(int idx, uint32_t w) {           // (a deferred slot resolved in place: unused by the kernels)
+#ifdef __CUDA_ARCH__
+        asm volatile("st.shared.b32 [%0], %1;" :: "r"(run_saddr + (uint32_t)idx * 4u), "r"(w) : "memory");
+#endif
+    }
+};
+struct RaggedGlobalSink {                                    // deferred slots go straight to the env's run in global memory
+    static constexpr bool PACKED = true, RAGGED = true;
+    uint32_t *run;
+    __device__ __forceinline__ void put_canon(int idx, uint32_t w) { run[idx] = w; }
+};
+template <int MODE> struct ResolveSink { using type = GlobalSink<MODE>; };
+template <> struct ResolveSink<4> { using type = RaggedGlobalSink; };
+// `at` = the env index (40-slot forms) or the word offset of the env's run (distinct-placements form)
+template <int MODE>
+__device__ __forceinline__ typename ResolveSink<MODE>::type make_resolve_sink(uint32_t at, uint32_t n, uint32_t *words, uint8_t *flags,
+                                                                              float4 *ff, uint32_t one) {
+    if constexpr (MODE == 4) return RaggedGlobalSink{words + at};
+    else return GlobalSink<MODE>{words + at, flags + at, ff + at, n, one, nullptr};
+}
+
 // ---- warp-private queues of deferred (row-completing) slots ---------------------------------------------------------
 // Only ~2 lanes of a warp have such a slot in any given tile, so resolving them in place runs the ~300-instruction general
 // move at a few % lane utilisation, and pooling them per CTA (the previous design) costs two block-wide barriers per tile:
@@ -232,11 +283,13 @@ struct WarpQueue {
 };
 struct WqPos { uint32_t head, tail, ehead, etail; };      // warp-uniform, monotonically increasing (indices are taken modulo)
 
+__device__ __forceinline__ void rag_wait(bool complete);
 template <int MODE>
 __device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, const uint4 *s_tab, uint32_t *scr, uint32_t n,
                                            uint32_t *words, uint8_t *flags, float4 *ff, int L, uint32_t one) {
     const uint32_t lane = threadIdx.x & 31u;
     while (p.tail - p.head >= 32u || (flush && p.tail != p.head)) {
+        if constexpr (MODE == 4) rag_wait(true);
         const uint32_t live = p.tail - p.head, take = live < 32u ? live : 32u;
         if (lane < take) {
             const uint32_t item = q.items[(p.head + lane) % WQ_ITEMS], entry = item & 63u, slot = item >> 6;
@@ -245,8 +298,7 @@ __device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, c
             for (int j = 0; j < COLS; ++j) cols[j] = q.env[j * WQ_ENVS + entry];
             const uint32_t m0 = q.env[10 * WQ_ENVS + entry];
             const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, q.env[11 * WQ_ENVS + entry], m0 >> 16};
-            const uint32_t i = q.env[12 * WQ_ENVS + entry];
-            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, one, nullptr};
+            auto sink = make_resolve_sink<MODE>(q.env[12 * WQ_ENVS + entry], n, words, flags, ff, one);
             resolve_slot(cols, cx, (int)slot, s_tab, scr, THREADS, L, sink);
         }
         __syncwarp();
@@ -256,7 +308,8 @@ __device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, c
     }
 }
 
-// every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer)
+// every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer); `i` = env index, or in the
+// distinct-placements form the word offset of the env's run
 template <int MODE>
 __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e, const PendingCtx &cx, uint32_t i,
                                            const uint4 *s_tab, uint32_t *scr, uint32_t n, uint32_t *words, uint8_t *flags,
@@ -287,7 +340,7 @@ __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e,
                 q.items[at++ % WQ_ITEMS] = (uint16_t)(entry | ((uint32_t)sl << 6));
             }
         } else {                                                       // queue full: this lane resolves its own slots now
-            GlobalSink<MODE> sink{words + i, flags + i, ff + i, n, one, nullptr};
+            auto sink = make_resolve_sink<MODE>(i, n, words, flags, ff, one);
             unsigned long long m = cx.mask;
             while (m) {
                 const int sl = __ffsll((long long)m) - 1;
@@ -302,6 +355,61 @@ __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e,
     }
     __syncwarp();
     wq_resolve<MODE>(q, p, false, s_tab, scr, n, words, flags, ff, L, one);
+}
+
+// ---- distinct-placements form: the two warp-collective halves around the enumeration of a tile
+struct RagTile { uint32_t excl, total, tb; };
+// cnt = this lane's run length (0 / 9 / 17 / 34): exclusive prefix over the warp, and one atomicAdd reserving the tile's
+// words (rounded up to 4 so that every tile starts 16-byte aligned); the returned base is only needed after the enumeration
+__device__ __forceinline__ RagTile rag_reserve(uint32_t cnt, uint32_t *cursor) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    RagTile t;
+    t.excl = incl - cnt;
+    t.total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    t.tb = 0u;
+    if (lane == 0u && t.total) t.tb = atomicAdd(cursor, (t.total + 3u) & ~3u);
+    return t;
+}
+// staging area -> rows[tile base ...] with 16-byte stores; returns the tile base (word offset).  The trailing __syncwarp orders
+// these stores before the deferred-slot resolver's (other lanes of this warp write single words of the same runs later)
+// and lets the next tile reuse the staging area.
+#ifndef TPL_RAG_TMA
+#define TPL_RAG_TMA 0               // tuning knob: move the staged tile with one bulk copy (TMA engine) instead of a store loop
+#endif
+__device__ __forceinline__ uint32_t rag_flush(uint32_t *stage, const RagTile &t, uint32_t *rows) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tb = __shfl_sync(0xFFFFFFFFu, t.tb, 0);
+    const uint32_t ta = (t.total + 3u) & ~3u;
+    if (lane < ta - t.total) stage[t.total + lane] = 0u;                     // the alignment gap holds zeros, not stale words
+#if TPL_RAG_TMA
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // this lane's staging writes -> visible to the bulk engine
+    __syncwarp();
+    if (lane == 0u && ta) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(rows + tb), "r"(sa), "r"(ta * 4u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+#else
+    __syncwarp();
+    for (uint32_t k = lane * 4u; k < ta; k += 128u)
+        *reinterpret_cast<uint4 *>(rows + tb + k) = *reinterpret_cast<const uint4 *>(stage + k);
+    __syncwarp();
+#endif
+    return tb;
+}
+// bulk-copy variant only: the staging area may be rewritten once the engine has READ it; the deferred-slot resolver may
+// write single words of a flushed run once the copy is COMPLETE (both are waits of the issuing lane, then a warp sync)
+__device__ __forceinline__ void rag_wait(bool complete) {
+#if TPL_RAG_TMA
+    if ((threadIdx.x & 31u) == 0u) {
+        if (complete) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr)); }
@@ -331,10 +439,19 @@ __device__ __forceinline__ void stage_take(RecordStage &rs, Env &e) {
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
 #endif
+// piece and run length (distinct placements) of the env's current piece; 7 / 0 when the queue is empty
+__device__ __forceinline__ void current_run(const Env &e, const uint4 *tab, uint32_t &piece, uint32_t &cnt) {
+    piece = 7u; cnt = 0u;
+    if (e.head < e.npieces) { piece = queue_piece(e.q, e.head); cnt = orient_run_len(tab[piece * 8 + 1]); }
+}
+
 template <int MODE, bool P32 = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
-                   uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
+                   uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one,
+                   uint32_t *__restrict__ runs, uint32_t run_base, uint32_t *cursor, uint32_t *cursor_clear) {
+    constexpr bool RAG = (MODE == 4);
+    extern __shared__ __align__(16) uint32_t s_rag[];                 // RAG: one staging area per warp (RAG_SMEM_BYTES)
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
@@ -342,6 +459,8 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
     __shared__ RecordStage s_stage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
     RecordStage &rs = s_stage[threadIdx.x >> 5];
+    uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
+    if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
     int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
@@ -352,11 +471,26 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
         Env e;
         stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
         if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
-        if (i < n) {
-            GlobalSink<MODE, P32> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+        if constexpr (RAG) {
+            uint32_t piece = 7u, cnt = 0u;
+            if (i < n) current_run(e, s_tab, piece, cnt);
+            const RagTile rt = rag_reserve(cnt, cursor);
+            rag_wait(false);
+            if (i < n) {
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+                RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+            }
+            const uint32_t goff = rag_flush(stage, rt, words) + rt.excl;
+            if (i < n) runs[i] = (goff + run_base) | (piece << 29);       // (the resolver addresses `words + goff`: call-local)
+            wq_publish<MODE>(q, qp, e, cx, goff, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
+        } else {
+            if (i < n) {
+                GlobalSink<MODE, P32> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+            }
+            wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
         }
-        wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
     }
     wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
 }
@@ -398,7 +532,7 @@ constexpr int TILE = 2 * ST;                              // envs per tile
 constexpr int SORT_SMEM_BYTES = 40 * TILE * 4 + SCR_ROWS * ST * 4 + TAB_WORDS4 * 16 + TILE * 2 + 64;
 
 struct TileSink {                                          // packed words at the env's original column of the tile
-    static constexpr bool PACKED = true;
+    static constexpr bool PACKED = true, RAGGED = false;
     uint32_t *out;                                         // s_out + original local id
     uint32_t *orot;
     __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * TILE; }
@@ -522,8 +656,11 @@ template <int MODE, bool P32 = false>
 __global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
-                    const uint4 *__restrict__ pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
-                    uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M, uint32_t one) {
+                    const uint4 *__restrict__ pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count,
+                    uint32_t *__restrict__ words, uint8_t *__restrict__ aflags, float4 *__restrict__ ff, int L, int M, uint32_t one,
+                    uint32_t *__restrict__ runs, uint32_t run_base, uint32_t *cursor, uint32_t *cursor_clear) {
+    constexpr bool RAG = (MODE == 4);
+    extern __shared__ __align__(16) uint32_t s_rag[];                 // RAG: one staging area per warp (RAG_SMEM_BYTES)
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
@@ -531,6 +668,8 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
     __shared__ RecordStage s_stage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
     RecordStage &rs = s_stage[threadIdx.x >> 5];
+    uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
+    if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
@@ -571,6 +710,7 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
             }
             if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {            // TPL_RESET_DONE semantics
                 if (episode) episode[i] = ep1;
+                if (tstep) tstep[i] = 0u;                                           // a new episode: the action stream of the rollouts restarts
                 install_config(e, pool, kcfg, seed, env_base + (uint64_t)i, ep1, gen_count);
                 acc[7] += 1;
                 changed = true;
@@ -581,13 +721,60 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
                 st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
             }
             st[3 * stride + i] = pack_meta(e);
-            GlobalSink<MODE, P32> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
-            afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
         }
-        wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
+        if constexpr (RAG) {
+            uint32_t piece = 7u, cnt = 0u;
+            if (i < n) current_run(e, s_tab, piece, cnt);
+            const RagTile rt = rag_reserve(cnt, cursor);
+            rag_wait(false);
+            if (i < n) {
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+                RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+            }
+            const uint32_t goff = rag_flush(stage, rt, words) + rt.excl;
+            if (i < n) runs[i] = (goff + run_base) | (piece << 29);       // (the resolver addresses `words + goff`: call-local)
+            wq_publish<MODE>(q, qp, e, cx, goff, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
+        } else {
+            if (i < n) {
+                GlobalSink<MODE, P32> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
+                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+            }
+            wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
+        }
     }
     wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
     if (stats) flush_stats(acc, stats);
+}
+
+// =================================================================================================
+// distinct placements -> the 40-slot grid (compact form): slot (r, c) of env i is placement
+// (r % n_rot, min(c, 10 - w)) of its run (game/tetris.py:61, :364), with TPL_FLAG_ALIAS set when that differs from (r, c)
+// =================================================================================================
+__global__ void __launch_bounds__(THREADS)
+expand_distinct_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ runs, int n, uint32_t *__restrict__ words) {
+    __shared__ uint4 s_tab[TAB_WORDS4];
+    load_table(s_tab);
+    const int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t d = runs[i], piece = d >> 29;
+    const uint32_t *run = rows + (d & 0x1FFFFFFFu);
+    for (int r = 0; r < 4; ++r) {
+        uint32_t rb = 0, cmax = 0, nrot = 1;
+        if (piece < 7u) {
+            nrot = (uint32_t)orient_nrot(s_tab[piece * 8]);
+            const uint4 o = s_tab[(piece * 4 + (uint32_t)r % nrot) * 2], ob = s_tab[(piece * 4 + (uint32_t)r % nrot) * 2 + 1];
+            rb = orient_rot_base(ob); cmax = (uint32_t)(COLS - orient_w(o));
+        }
+        for (int c = 0; c < COLS; ++c) {
+            uint32_t w = F_NOPIECE << 3;
+            if (piece < 7u) {
+                const uint32_t cc = (uint32_t)c < cmax ? (uint32_t)c : cmax;
+                w = run[rb + cc] | (((uint32_t)r >= nrot || cc != (uint32_t)c) ? (F_ALIAS << 3) : 0u);
+            }
+            words[(size_t)(r * 10 + c) * (size_t)n + (size_t)i] = w;
+        }
+    }
 }
 
 // =================================================================================================
@@ -729,13 +916,20 @@ static inline unsigned grid_for(int n) { return (unsigned)((n + THREADS - 1) / T
 
 // Grid-stride kernels: at most `blocks_per_sm` resident CTAs per SM, i.e. a multiple of the SM count (148 on
 // B200), so per-CTA set-up and the statistics flush are paid once per CTA slot instead of once per 128 envs.
+// Cached per device: the launches below go to the CUDA *current* device, which need not be the one the first call saw.
+struct DevInfo { int sms, occ_step, occ_as, occ_so, occ_sod, occ_asd; };
+static DevInfo &dev_info() {
+    static DevInfo info[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    return info[(dev >= 0 && dev < 64) ? dev : 0];
+}
 static int sm_count() {
-    static int sms = 0;
-    if (!sms) {
+    DevInfo &d = dev_info();
+    if (!d.sms) {
         int dev = 0; cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sms <= 0) d.sms = 148;
     }
-    return sms;
+    return d.sms;
 }
 
 // The piece-sorted afterstate kernel (opt-in: TPL_SORTED_AFTERSTATES=1) moves its output tile with 16-byte-granular
@@ -762,6 +956,67 @@ static unsigned grid_persistent(int n, int blocks_per_sm) {
     if (blocks_per_sm <= 0) blocks_per_sm = 16;
     const unsigned need = grid_for(n), cap = (unsigned)(sms * blocks_per_sm);
     return need < cap ? need : cap;
+}
+
+// distinct-placements argument checks shared by the two entry points
+static int check_distinct(const char *who, int n, const uint32_t *rows, int64_t rows_capacity, const uint32_t *runs, const uint32_t *cursor2,
+                          int phase) {
+    if (!rows || !runs || !cursor2) return fail(TPL_EINVAL, "%s: rows / runs / cursor2 must not be null", who);
+    if (phase != 0 && phase != 1) return fail(TPL_EINVAL, "%s: phase must be 0 or 1", who);
+    if (n > (1 << 23)) return fail(TPL_ERANGE, "%s: at most 2^23 envs per call (29-bit run offsets)", who);
+    if (rows_capacity < TPL_DISTINCT_CAPACITY(n)) return fail(TPL_ERANGE, "%s: rows_capacity %lld < TPL_DISTINCT_CAPACITY(n) = %lld words", who,
+                                                             (long long)rows_capacity, (long long)TPL_DISTINCT_CAPACITY(n));
+    if (((uintptr_t)rows & 15u) != 0) return fail(TPL_EINVAL, "%s: rows must be 16-byte aligned", who);
+    return 0;
+}
+template <class KernelT>
+static int allow_rag_smem(KernelT kernel, const char *who) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RAG_SMEM_BYTES);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+    return 0;
+}
+
+static int step_observe_impl(const char *who, void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines,
+                             uint8_t *flags, int8_t *st, long long *stats, const void *pool, int K, uint32_t *episode, uint32_t *tstep,
+                             uint64_t seed, uint64_t env_base, int gen_count, uint8_t *feats, uint8_t *aflags, float *feats_f32,
+                             uint32_t *rows, uint32_t *runs, uint32_t run_base, uint32_t *cursor2, int phase, int L, int M, void *stream) {
+    if (n < 0 || !state || !rot || !loc) return fail(TPL_EINVAL, "%s: null argument", who);
+    if (plane_stride < n) return fail(TPL_ERANGE, "%s: plane_stride < n", who);
+    if (n > (1 << 25)) return fail(TPL_ERANGE, "%s: at most 2^25 envs per call (32-bit output offsets)", who);
+    if (pool && K <= 0) return fail(TPL_EINVAL, "%s: pool given but K <= 0", who);
+    if (gen_count < 0 || gen_count > TPL_MAX_PIECES) return fail(TPL_ERANGE, "%s: gen_count %d > 42", who, gen_count);
+    if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "%s: L/M out of range", who);
+    if (n == 0) return 0;
+    const cudaStream_t s = (cudaStream_t)stream;
+    uint4 *sp = (uint4 *)state; const uint4 *pp = (const uint4 *)pool; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
+    unsigned long long *sq = (unsigned long long *)stats;
+    // exactly one resident wave of persistent CTAs (4 per SM at 128 registers): every warp walks through its share of the
+    // 32-env tiles, and the partly filled last round of its deferred-slot queue is paid once per warp
+    int &so_blocks_per_sm = rows ? dev_info().occ_sod : dev_info().occ_so;
+    if (rows) {
+        if (!so_blocks_per_sm) {
+            int rc = allow_rag_smem(step_observe_kernel<4>, who); if (rc) return rc;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<4>, THREADS, RAG_SMEM_BYTES) != cudaSuccess || so_blocks_per_sm <= 0)
+                so_blocks_per_sm = 4;
+        }
+        step_observe_kernel<4><<<grid_persistent(n, so_blocks_per_sm), THREADS, RAG_SMEM_BYTES, s>>>(
+            sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, seed, env_base, gen_count, rows, nullptr, nullptr, L, M, 1u,
+            runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
+        return check_launch(who);
+    }
+    if (!so_blocks_per_sm &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<0>, THREADS, 0) != cudaSuccess || so_blocks_per_sm <= 0))
+        so_blocks_per_sm = 4;
+    const unsigned g = grid_persistent(n, so_blocks_per_sm);
+#define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, \
+                                                                    seed, env_base, gen_count, w, aflags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr)
+    if (feats && !aflags && one_window(feats, n)) TPL_SO(0, true);
+    else if (feats && !aflags) TPL_SO(0);
+    else if (feats && !feats_f32) TPL_SO(1);
+    else if (!feats) TPL_SO(2);
+    else TPL_SO(3);
+#undef TPL_SO
+    return check_launch(who);
 }
 
 extern "C" {
@@ -792,7 +1047,7 @@ int tpl_unpack(const void *state, int64_t plane_stride, int n, uint16_t *rows, u
 }
 
 int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *pool, int K, const int32_t *idx,
-                        const uint8_t *mask, int mode, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count,
+                        const uint8_t *mask, int mode, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count,
                         void *stream) {
     if (n < 0 || !state || !pool || K <= 0) return fail(TPL_EINVAL, "tpl_reset_from_pool: null state/pool or K <= 0");
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_reset_from_pool: plane_stride < n");
@@ -801,7 +1056,7 @@ int tpl_reset_from_pool(void *state, int64_t plane_stride, int n, const void *po
     if (gen_count < 0 || gen_count > TPL_MAX_PIECES) return fail(TPL_ERANGE, "tpl_reset_from_pool: gen_count %d > 42", gen_count);
     if (n == 0) return 0;
     reset_kernel<<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, (const uint4 *)pool, K, idx,
-                                                                     mask, mode, episode, seed, env_base, gen_count);
+                                                                     mask, mode, episode, tstep, seed, env_base, gen_count);
     return check_launch("tpl_reset_from_pool");
 }
 
@@ -811,7 +1066,7 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
     if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step: plane_stride < n");
     if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step: L/M out of range");
     if (n == 0) return 0;
-    static int step_blocks_per_sm = 0;                 // exactly one resident wave: no partial second wave at the tail
+    int &step_blocks_per_sm = dev_info().occ_step;     // exactly one resident wave: no partial second wave at the tail
     if (!step_blocks_per_sm &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&step_blocks_per_sm, step_kernel, THREADS, 0) != cudaSuccess || step_blocks_per_sm <= 0))
         step_blocks_per_sm = 8;
@@ -830,17 +1085,15 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
     if (n == 0) return 0;
     const cudaStream_t s = (cudaStream_t)stream;
     const uint4 *st = (const uint4 *)state; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
-    static int as_blocks_per_sm = 0;                   // one resident wave, as for the fused kernel
+    int &as_blocks_per_sm = dev_info().occ_as;         // one resident wave, as for the fused kernel
     if (!as_blocks_per_sm &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&as_blocks_per_sm, afterstates_kernel<0>, THREADS, 0) != cudaSuccess || as_blocks_per_sm <= 0))
         as_blocks_per_sm = 4;
     const unsigned g = grid_persistent(n, as_blocks_per_sm);
     if (feats && !flags && !feats_f32 && sorted_path_ok(n, feats)) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        {   // per device and cheap; this path is an opt-in experiment
             cudaError_t e = cudaFuncSetAttribute(afterstates_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
             if (e != cudaSuccess) return fail((int)e, "tpl_afterstates: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            attr_set = true;
         }
         const int ntiles = (n + TILE - 1) / TILE;
         const unsigned gs = (unsigned)(ntiles < 4 * sm_count() ? ntiles : 4 * sm_count());
@@ -855,45 +1108,71 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
         else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
         return check_launch("tpl_afterstates(split)");
     }
-    if (feats && !flags && one_window(feats, n)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
-    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
-    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
-    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
-    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
+    if (feats && !flags && one_window(feats, n)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
     return check_launch("tpl_afterstates");
 }
 
 int tpl_step_observe(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
-                     int8_t *st, long long *stats, const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base,
-                     int gen_count, uint8_t *feats, uint8_t *aflags, float *feats_f32, int L, int M, void *stream) {
-    if (n < 0 || !state || !rot || !loc) return fail(TPL_EINVAL, "tpl_step_observe: null argument");
-    if (plane_stride < n) return fail(TPL_ERANGE, "tpl_step_observe: plane_stride < n");
-    if (n > (1 << 25)) return fail(TPL_ERANGE, "tpl_step_observe: at most 2^25 envs per call (32-bit output offsets)");
-    if (pool && K <= 0) return fail(TPL_EINVAL, "tpl_step_observe: pool given but K <= 0");
-    if (gen_count < 0 || gen_count > TPL_MAX_PIECES) return fail(TPL_ERANGE, "tpl_step_observe: gen_count %d > 42", gen_count);
+                     int8_t *st, long long *stats, const void *pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed,
+                     uint64_t env_base, int gen_count, uint8_t *feats, uint8_t *aflags, float *feats_f32, int L, int M, void *stream) {
     if (!feats && !feats_f32) return fail(TPL_EINVAL, "tpl_step_observe: no feature output requested");
     if (feats_f32 && !aflags) return fail(TPL_EINVAL, "tpl_step_observe: the float form needs the flags array");
-    if (L < 0 || M < 0 || M > 65535 || L > 65535) return fail(TPL_ERANGE, "tpl_step_observe: L/M out of range");
+    return step_observe_impl("tpl_step_observe", state, plane_stride, n, rot, loc, dlines, flags, st, stats, pool, K, episode, tstep, seed,
+                             env_base, gen_count, feats, aflags, feats_f32, nullptr, nullptr, 0u, nullptr, 0, L, M, stream);
+}
+
+int tpl_step_observe_distinct(void *state, int64_t plane_stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines,
+                              uint8_t *flags, int8_t *st, long long *stats, const void *pool, int K, uint32_t *episode, uint32_t *tstep,
+                              uint64_t seed, uint64_t env_base, int gen_count, uint32_t *rows, int64_t rows_capacity, uint32_t *runs,
+                              uint32_t run_base, uint32_t *cursor2, int phase, int L, int M, void *stream) {
+    int rc = check_distinct("tpl_step_observe_distinct", n, rows, rows_capacity, runs, cursor2, phase); if (rc) return rc;
+    return step_observe_impl("tpl_step_observe_distinct", state, plane_stride, n, rot, loc, dlines, flags, st, stats, pool, K, episode, tstep,
+                             seed, env_base, gen_count, nullptr, nullptr, nullptr, rows, runs, run_base, cursor2, phase, L, M, stream);
+}
+
+int tpl_afterstates_distinct(const void *state, int64_t plane_stride, int n, uint32_t *rows, int64_t rows_capacity, uint32_t *runs,
+                             uint32_t run_base, uint32_t *cursor2, int phase, int L, int M, void *stream) {
+    if (n < 0 || !state) return fail(TPL_EINVAL, "tpl_afterstates_distinct: null state");
+    if (plane_stride < n) return fail(TPL_ERANGE, "tpl_afterstates_distinct: plane_stride < n");
+    int rc = check_distinct("tpl_afterstates_distinct", n, rows, rows_capacity, runs, cursor2, phase); if (rc) return rc;
     if (n == 0) return 0;
-    const cudaStream_t s = (cudaStream_t)stream;
-    uint4 *sp = (uint4 *)state; const uint4 *pp = (const uint4 *)pool; uint32_t *w = (uint32_t *)feats; float4 *f = (float4 *)feats_f32;
-    unsigned long long *sq = (unsigned long long *)stats;
-    // exactly one resident wave of persistent CTAs (4 per SM at 128 registers): every warp walks through its share of the
-    // 32-env tiles, and the partly filled last round of its deferred-slot queue is paid once per warp
-    static int so_blocks_per_sm = 0;
-    if (!so_blocks_per_sm &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<0>, THREADS, 0) != cudaSuccess || so_blocks_per_sm <= 0))
-        so_blocks_per_sm = 4;
-    const unsigned g = grid_persistent(n, so_blocks_per_sm);
-#define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, \
-                                                                    seed, env_base, gen_count, w, aflags, f, L, M, 1u)
-    if (feats && !aflags && one_window(feats, n)) TPL_SO(0, true);
-    else if (feats && !aflags) TPL_SO(0);
-    else if (feats && !feats_f32) TPL_SO(1);
-    else if (!feats) TPL_SO(2);
-    else TPL_SO(3);
-#undef TPL_SO
-    return check_launch("tpl_step_observe");
+    int &bps = dev_info().occ_asd;
+    if (!bps) {
+        rc = allow_rag_smem(afterstates_kernel<4>, "tpl_afterstates_distinct"); if (rc) return rc;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, afterstates_kernel<4>, THREADS, RAG_SMEM_BYTES) != cudaSuccess || bps <= 0) bps = 4;
+    }
+    afterstates_kernel<4><<<grid_persistent(n, bps), THREADS, RAG_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const uint4 *)state, plane_stride, n, rows, nullptr, nullptr, L, M, 1u, runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
+    return check_launch("tpl_afterstates_distinct");
+}
+
+void tpl_distinct_tables(uint8_t *count, uint8_t *slot_of, uint8_t *canon_of) {
+    constexpr OrientTable t = make_table();
+    for (int p = 0; p < 7; ++p) {
+        const int nrot = (int)((t.e[p * 4].ax >> 24) & 3u) + 1;
+        if (count) count[p] = (uint8_t)((t.e[p * 4].bw >> 8) & 0xFFu);
+        if (slot_of) for (int j = 0; j < TPL_DISTINCT_MAX; ++j) slot_of[p * TPL_DISTINCT_MAX + j] = 255;
+        for (int r = 0; r < 4; ++r) {
+            const OrientEntry &e = t.e[p * 4 + r % nrot];
+            const int w = (int)((e.ax >> 16) & 7u), rb = (int)(e.bw & 0xFFu);
+            for (int c = 0; c < COLS; ++c) {
+                const int cc = c < COLS - w ? c : COLS - w;
+                if (canon_of) canon_of[p * 40 + r * 10 + c] = (uint8_t)(rb + cc);
+                if (slot_of && r < nrot && c == cc) slot_of[p * TPL_DISTINCT_MAX + rb + c] = (uint8_t)(r * 10 + c);
+            }
+        }
+    }
+}
+
+int tpl_expand_distinct(const uint32_t *rows, const uint32_t *runs, int n, uint8_t *feats, void *stream) {
+    if (n < 0 || !rows || !runs || !feats) return fail(TPL_EINVAL, "tpl_expand_distinct: null argument");
+    if (n == 0) return 0;
+    expand_distinct_kernel<<<grid_for(n), THREADS, 0, (cudaStream_t)stream>>>(rows, runs, n, (uint32_t *)feats);
+    return check_launch("tpl_expand_distinct");
 }
 
 int tpl_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode, uint32_t episode0,

@@ -74,6 +74,8 @@ class HostBatchedTetris:
         rows = np.ascontiguousarray(pool.rows, np.uint16)
         pieces = np.ascontiguousarray(pool.pieces, np.uint8)
         npieces = np.ascontiguousarray(pool.npieces, np.uint8)
+        if int(pieces.max(initial=0)) > 6 or int(npieces.max(initial=0)) > min(MAX_PIECES, pieces.shape[1]):
+            raise ValueError("pool: piece ids must be 0..6 and npieces <= min(42, pieces per row)")
         _lib.check(self._L.tpl_env_set_pool(self._h, rows.shape[0], _p(rows), _p(pieces), pieces.shape[1], _p(npieces)),
                    "tpl_env_set_pool")
 
@@ -90,6 +92,8 @@ class HostBatchedTetris:
         npieces = np.ascontiguousarray(npieces, np.uint8).reshape(n)
         if int(npieces.max(initial=0)) > min(MAX_PIECES, pieces.shape[1]):
             raise ValueError("npieces exceeds the 42-piece queue or the pieces array")
+        if int(pieces.max(initial=0)) > 6:
+            raise ValueError("piece ids must be 0..6")
         c = lambda x, dt: np.ascontiguousarray(x, dt).reshape(n) if x is not None else None   # noqa: E731
         lines, moves, state, head = c(lines, np.int32), c(moves, np.int32), c(state, np.int8), c(head, np.uint8)
         _lib.check(self._L.tpl_env_load(self._h, _p(rows), _p(pieces), pieces.shape[1], _p(npieces), _p(lines), _p(moves),
@@ -132,6 +136,22 @@ class HostBatchedTetris:
         feats, flags = np.empty((40, n, 4), np.uint8), np.empty((40, n), np.uint8)
         _lib.check(self._L.tpl_env_afterstates(self._h, _p(feats), _p(flags)), "tpl_env_afterstates")
         return feats.reshape(4, 10, n, 4).transpose(2, 0, 1, 3), flags.reshape(4, 10, n).transpose(2, 0, 1)
+
+    def distinct_capacity(self) -> int:
+        """words the ``rows`` buffer of ``step_observe_distinct`` must hold (chunk regions included)"""
+        return int(self._L.tpl_env_distinct_capacity(self._h))
+
+    def chunks(self) -> int:
+        return int(self._L.tpl_env_chunks(self._h))
+
+    def step_observe_distinct(self, rot: np.ndarray, loc: np.ndarray, dlines: np.ndarray, flags: np.ndarray, state: np.ndarray,
+                              rows: np.ndarray, runs: np.ndarray) -> int:
+        """``step_observe`` with the afterstates in the distinct-placements form: ``rows`` uint32[distinct_capacity()],
+        ``runs`` uint32[N] (see ``distinct.expand``).  Returns the number of ``rows`` words that crossed PCIe."""
+        words = ctypes.c_int64(0)
+        _lib.check(self._L.tpl_env_step_observe_distinct(self._h, _p(rot), _p(loc), _p(dlines), _p(flags), _p(state), _p(rows),
+                                                         rows.size, _p(runs), ctypes.byref(words)), "tpl_env_step_observe_distinct")
+        return int(words.value)
 
     def step_observe(self, rot: np.ndarray, loc: np.ndarray, dlines: np.ndarray, flags: np.ndarray, state: np.ndarray,
                      feats: Optional[np.ndarray], aflags: Optional[np.ndarray]) -> None:

@@ -184,6 +184,8 @@ class Tetris:
             raise IndexError("pop from empty list")
         if location < 0:
             raise ValueError("negative location")
+        if not 0 <= int(self.pieces[0]) <= 6:                 # the reference indexes `tetrominos[piece]` (:60-61)
+            raise IndexError("tuple index out of range")
         dl, fl = self._run_move(rotations, location)
         f = self._env.fields(queue=False)
         self.pieces.pop(0)
@@ -207,7 +209,9 @@ class Tetris:
         self._sync_limits()
         n = min(len(self.pieces), MAX_PIECES)
         p = np.zeros((1, MAX_PIECES), np.uint8)
-        p[0, :n] = self.pieces[:n]
+        # `pieces` is a public mutable list: an id outside 0..6 further down the queue is harmless until it reaches the front
+        # (move() raises there like the reference); the upload itself only takes valid ids
+        p[0, :n] = [q if 0 <= q <= 6 else 0 for q in self.pieces[:n]]
         self._env.load(rows_from_bool(self.board)[None], p, np.array([n], np.uint8),
                        lines=[min(int(self.lines_cleared), 65535)], moves=[min(int(self.moves_used), 65535)],
                        state=[_state_to_code(self.state)])
@@ -228,9 +232,11 @@ class Tetris:
     def afterstates(self):
         """(feats uint8[4,10,4] = (rows cleared, holes, bumpiness, aggregate height), flags uint8[4,10])."""
         self._sync_limits()
+        if self.pieces and not 0 <= int(self.pieces[0]) <= 6:
+            raise IndexError("tuple index out of range")
         n = min(len(self.pieces), MAX_PIECES)
         p = np.zeros((1, MAX_PIECES), np.uint8)
-        p[0, :n] = self.pieces[:n]
+        p[0, :n] = [q if 0 <= q <= 6 else 0 for q in self.pieces[:n]]
         self._env.load(rows_from_bool(self.board)[None], p, np.array([n], np.uint8),
                        lines=[min(int(self.lines_cleared), 65535)], moves=[min(int(self.moves_used), 65535)],
                        state=[_state_to_code(self.state)])

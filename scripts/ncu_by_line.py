@@ -5,7 +5,7 @@ import collections, csv, glob, os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, pat = sys.argv[1], sys.argv[2]
-lib = glob.glob(os.path.join(ROOT, "*_b200", "csrc", "libtetris_piclim_sm100.so"))[0]
+lib = os.path.join(ROOT, "lib", "libtetris_piclim_sm100.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "piclim_kernels.sm_100a.cubin", lib], cwd=tmp, capture_output=True)
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, "piclim_kernels.sm_100a.cubin")], capture_output=True, text=True).stdout

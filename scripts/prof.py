@@ -1,6 +1,6 @@
 """Short, deterministic driver for ncu captures: W warm-up + K timed passes of one part of the hot path at 2^20 envs.
 
-    python scripts/prof.py --what pipeline|rollout_random|rollout_greedy|afterstates_f32 [--steps K] [--envs N]
+    python scripts/prof.py --what pipeline|fused|fused_distinct|afterstates_distinct|rollout_random|rollout_greedy|afterstates_f32 [--steps K] [--envs N]
 """
 import argparse
 import os
@@ -42,6 +42,10 @@ for i in range(tot):
         env.afterstates(f32=True, u8=False); env.move(rot[i], loc[i]); env.reset(done_only=True)
     elif a.what == "fused":
         env.step_observe(rot[i], loc[i], packed=True)
+    elif a.what == "fused_distinct":
+        env.step_observe_distinct(rot[i], loc[i])
+    elif a.what == "afterstates_distinct":
+        env.afterstates_distinct(); env.move(rot[i], loc[i]); env.reset(done_only=True)
     elif a.what == "rollout_random":
         env.rollout_random(32)
     elif a.what == "rollout_greedy":

@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = glob.glob(os.path.join(ROOT, "*_b200", "csrc", "libtetris_piclim_sm100.so"))[0]
+lib = os.path.join(ROOT, "lib", "libtetris_piclim_sm100.so")
 pat = sys.argv[1]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 ins, on = [], False

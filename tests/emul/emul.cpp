@@ -13,7 +13,7 @@ using namespace tpl;
 static const uint4 *table() { return reinterpret_cast<const uint4 *>(&c_orient); }
 
 struct HostSink {
-    static constexpr bool PACKED = false;
+    static constexpr bool PACKED = false, RAGGED = false;
     uint32_t *feats; uint8_t *flags; float *ff; size_t n, i;
     void put(int slot, uint32_t word, uint32_t fl) {
         const size_t o = (size_t)slot * n + i;
@@ -26,7 +26,7 @@ struct HostSink {
 
 // sink with copy(): the packed staging the sorted kernel uses (word | flags << 3), one row of 40 per env
 struct PackedRowSink {
-    static constexpr bool PACKED = true;
+    static constexpr bool PACKED = true, RAGGED = false;
     uint32_t row[40];
     int rot;
     void begin_rotation(int r) { rot = r; }
@@ -37,7 +37,47 @@ struct PackedRowSink {
     void copy(int dst, int src, uint32_t extra) { row[dst] = row[src] | (extra << 3); }
 };
 
+// distinct-placements form: the run of one env (at most 34 words); alias rotations write to a dummy row
+struct HostRaggedSink {
+    static constexpr bool PACKED = true, RAGGED = true;
+    uint32_t row[34 + 10];
+    uint32_t *prow;
+    void begin_rotation_ragged(bool canon, uint32_t rot_base) { prow = canon ? row + rot_base : row + 34; }
+    template <int C> void put_col(uint32_t w) { prow[C] = w; }
+    void put_canon(int idx, uint32_t w) { row[idx] = w; }
+};
+
+static uint32_t emul_distinct_env(const Env &e, int L, int M, int defer, uint32_t *rows, uint32_t &cursor, uint32_t run_base) {
+    uint32_t piece = 7u, cnt = 0u;
+    if (e.head < e.npieces) { piece = queue_piece(e.q, e.head); cnt = orient_run_len(table()[piece * 8 + 1]); }
+    HostRaggedSink sink; for (int s = 0; s < 44; ++s) sink.row[s] = 0xDEADBEEFu;
+    uint32_t scr[SCR_ROWS];
+    if (!defer) afterstates_env(e, table(), scr, 1, L, M, sink);
+    else {                                               // the kernels' way: deferred slots resolved afterwards, into the same run
+        PendingCtx cx;
+        afterstates_env(e, table(), scr, 1, L, M, sink, 0, 4, &cx);
+        unsigned long long m = cx.mask;
+        while (m) {
+            const int s = __builtin_ffsll((long long)m) - 1; m &= m - 1ull;
+            resolve_slot(e.col, cx, s, table(), scr, 1, L, sink);
+        }
+    }
+    const uint32_t off = cursor;
+    for (uint32_t j = 0; j < cnt; ++j) rows[off + j] = sink.row[j];
+    cursor += cnt;
+    return (off + run_base) | (piece << 29);
+}
+
 extern "C" {
+
+int emul_afterstates_distinct(const void *state, int64_t stride, int n, uint32_t *rows, uint32_t *runs, uint32_t run_base, uint32_t *cursor,
+                              int L, int M, int defer) {
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env((const uint4 *)state, stride, i, e);
+        runs[i] = emul_distinct_env(e, L, M, defer, rows, *cursor, run_base);
+    }
+    return 0;
+}
 
 // afterstates through the warp-uniform (alias-skipping) variant, each env being its own one-lane "warp".
 // defer != 0: the row-completing slots are returned by the enumeration and resolved afterwards, the way the
@@ -108,7 +148,7 @@ int emul_unpack(const void *state, int64_t stride, int n, uint16_t *rows, uint8_
 }
 
 int emul_reset_from_pool(void *state, int64_t stride, int n, const void *pool, int K, const int32_t *idx, const uint8_t *mask,
-                         int mode, uint32_t *episode, uint64_t seed, uint64_t env_base, int gen_count) {
+                         int mode, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count) {
     uint4 *st = (uint4 *)state;
     for (int64_t i = 0; i < n; ++i) {
         if (mode == 1 && !mask[i]) continue;
@@ -117,8 +157,9 @@ int emul_reset_from_pool(void *state, int64_t stride, int n, const void *pool, i
             const uint4 d = st[3 * stride + i];
             const uint32_t s = d.w & 0xFFu, head = (d.w >> 8) & 0xFFu, np = (d.w >> 16) & 0xFFu;
             if (s == S_RUNNING && head < np) continue;
-            ep += 1; if (episode) episode[i] = ep;
         }
+        if (mode == 2 || (mode == 1 && !idx)) { ep += 1; if (episode) episode[i] = ep; }
+        if (tstep) tstep[i] = 0u;
         uint32_t k;
         if (idx) { const int32_t v = idx[i]; k = (uint32_t)(v < 0 ? 0 : (v >= K ? K - 1 : v)); }
         else k = config_index(seed, env_base + (uint64_t)i, ep, K);
@@ -160,8 +201,9 @@ int emul_afterstates(const void *state, int64_t stride, int n, uint8_t *feats, u
 }
 
 int emul_step_observe(void *state, int64_t stride, int n, const uint8_t *rot, const uint8_t *loc, int8_t *dlines, uint8_t *flags,
-                      int8_t *sto, long long *stats, const void *pool, int K, uint32_t *episode, uint64_t seed, uint64_t env_base,
-                      int gen_count, uint8_t *feats, uint8_t *aflags, float *ff, int L, int M) {
+                      int8_t *sto, long long *stats, const void *pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed,
+                      uint64_t env_base, int gen_count, uint8_t *feats, uint8_t *aflags, float *ff, int L, int M,
+                      uint32_t *drows, uint32_t *druns, uint32_t *dcursor) {
     uint4 *st = (uint4 *)state;
     for (int64_t i = 0; i < n; ++i) {
         Env e; load_env(st, stride, i, e);
@@ -182,10 +224,12 @@ int emul_step_observe(void *state, int64_t stride, int n, const uint8_t *rot, co
         if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {
             uint32_t ep = episode ? episode[i] + 1u : 1u;
             if (episode) episode[i] = ep;
+            if (tstep) tstep[i] = 0u;
             install_config(e, (const uint4 *)pool, config_index(seed, env_base + (uint64_t)i, ep, K), seed, env_base + (uint64_t)i, ep, gen_count);
             if (stats) stats[7] += 1;
         }
         store_env(st, stride, i, e);
+        if (drows) { druns[i] = emul_distinct_env(e, L, M, (int)(i & 1), drows, *dcursor, 0u); continue; }
         HostSink sink{(uint32_t *)feats, aflags, ff, (size_t)n, (size_t)i};
         uint32_t scr2[SCR_ROWS];
         afterstates_env(e, table(), scr2, 1, L, M, sink);

@@ -41,13 +41,14 @@ class EmulEngine:
         sigs = {
             "pack": [P, I64, I, I, P, P, I, P, P, P, P, P],
             "unpack": [P, I64, I, P, P, P, P, P, P, P, P, P],
-            "reset_from_pool": [P, I64, I, P, I, P, P, I, P, U64, U64, I],
+            "reset_from_pool": [P, I64, I, P, I, P, P, I, P, P, U64, U64, I],
+            "afterstates_distinct": [P, I64, I, P, P, U32, P, I, I, I],
             "step": [P, I64, I, P, P, P, P, P, I, I],
             "afterstates": [P, I64, I, P, P, P, I, I],
             "afterstates_uniform": [P, I64, I, P, I, I, I],
             "afterstates_split": [P, I64, I, P, I, I],
             "gen_pieces": [P, I, I, U64, U64, P, U32],
-            "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, U64, U64, I, P, P, P, I, I],
+            "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, P, U64, U64, I, P, P, P, I, I, P, P, P],
             "rollout_random": [P, I64, I, P, I, P, P, P, I, U64, U64, I, I, I],
             "rollout_greedy": [P, I64, I, P, I, P, P, P, I, P, U64, U64, I, I, I],
         }
@@ -123,22 +124,37 @@ class EmulEngine:
         assert np.array_equal(spl, feats), "rotation-split afterstate variant differs from the plain one"
         return feats.reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
 
-    def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
+    def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0, tstep=None):
         idx = self._c(idx, np.int32); mask = self._c(mask, np.uint8)
         self.L.emul_reset_from_pool(_np_ptr(s.planes), s.stride, s.n, _np_ptr(pool), pool.shape[0], _np_ptr(idx), _np_ptr(mask),
-                                    mode, _np_ptr(episode), seed, env_base, gen_count)
+                                    mode, _np_ptr(episode), _np_ptr(tstep), seed, env_base, gen_count)
 
-    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False):
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False):
+        """distinct=True: the afterstates come back as (rows uint32[used], runs uint32[n]) in place of (feats, afl)."""
         n = s.n
         rot = np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8)
         loc = np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8)
         dl, fl, st = np.zeros(n, np.int8), np.zeros(n, np.uint8), np.zeros(n, np.int8)
         feats, afl = np.zeros((40, n, 4), np.uint8), (None if packed else np.zeros((40, n), np.uint8))
+        drows, druns, dcur = (np.zeros(34 * n + 4, np.uint32), np.zeros(n, np.uint32), np.zeros(1, np.uint32)) if distinct else (None, None, None)
         stats = np.zeros(8, np.int64)
         self.L.emul_step_observe(_np_ptr(s.planes), s.stride, n, _np_ptr(rot), _np_ptr(loc), _np_ptr(dl), _np_ptr(fl), _np_ptr(st),
-                                 _np_ptr(stats), _np_ptr(pool), pool.shape[0], _np_ptr(episode), seed, env_base, 0,
-                                 _np_ptr(feats), _np_ptr(afl), None, L, M)
+                                 _np_ptr(stats), _np_ptr(pool), pool.shape[0], _np_ptr(episode), _np_ptr(tstep), seed, env_base, 0,
+                                 _np_ptr(feats), _np_ptr(afl), None, L, M, _np_ptr(drows), _np_ptr(druns), _np_ptr(dcur))
+        if distinct:
+            return dl, fl, st, drows[:int(dcur[0])], druns, stats
         return dl, fl, st, feats, afl, stats
+
+    def afterstates_distinct(self, s, L, M):
+        """(rows uint32[used], runs uint32[n]); the in-place and the deferred resolution of row-completing slots must agree"""
+        n = s.n
+        out = []
+        for defer in (0, 1):
+            rows, runs, cur = np.zeros(34 * n + 4, np.uint32), np.zeros(n, np.uint32), np.zeros(1, np.uint32)
+            self.L.emul_afterstates_distinct(_np_ptr(s.planes), s.stride, n, _np_ptr(rows), _np_ptr(runs), 0, _np_ptr(cur), L, M, defer)
+            out.append((rows[:int(cur[0])], runs))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        return out[0]
 
     def gen_pieces(self, n, count, seed, env_base, episode0=0, episode=None):
         out = np.zeros((n, count), np.uint8)
@@ -259,30 +275,75 @@ class GpuEngine:
                   "tpl_afterstates(packed)")
         return feats.cpu().numpy().reshape(4, 10, s.n, 4).transpose(2, 0, 1, 3)
 
-    def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0):
+    def reset(self, s, pool, idx=None, mask=None, mode=0, episode=None, seed=0, env_base=0, gen_count=0, tstep=None):
         d_idx, d_mask = self._t(idx, np.int32), self._t(mask, np.uint8)
         d_ep = self._t(episode, np.uint32) if episode is not None else None
+        d_ts = self._t(tstep, np.uint32) if tstep is not None else None
         self._chk(self.L.tpl_reset_from_pool(self._p(s.planes), s.stride, s.n, self._p(pool), pool.shape[0], self._p(d_idx),
-                                             self._p(d_mask), mode, self._p(d_ep), seed, env_base, gen_count, self._stream()),
+                                             self._p(d_mask), mode, self._p(d_ep), self._p(d_ts), seed, env_base, gen_count, self._stream()),
                   "tpl_reset_from_pool")
         if episode is not None:
             episode[:] = d_ep.cpu().numpy().view(np.uint32)
+        if tstep is not None:
+            tstep[:] = d_ts.cpu().numpy().view(np.uint32)
 
-    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False):
+    def _distinct_args(self, n):
+        t = self.torch
+        cap = 34 * n + 4 * ((n + 31) // 32)
+        rows = t.full((cap,), -1, dtype=t.int32, device=self.dev)
+        runs = t.zeros(n, dtype=t.int32, device=self.dev)
+        if not hasattr(self, "_cursor2"):
+            self._cursor2, self._phase = t.zeros(2, dtype=t.int32, device=self.dev), 0
+        phase = self._phase; self._phase ^= 1
+        return rows, cap, runs, self._cursor2, phase
+
+    def _distinct_result(self, rows, runs, phase):
+        used = int(self._cursor2[phase].item())
+        assert int(self._cursor2[phase ^ 1].item()) == 0, "the kernel must clear the other phase's counter"
+        return rows.cpu().numpy().view(np.uint32)[:used], runs.cpu().numpy().view(np.uint32)
+
+    def afterstates_distinct(self, s, L, M):
+        rows, cap, runs, cur, phase = self._distinct_args(s.n)
+        self._chk(self.L.tpl_afterstates_distinct(self._p(s.planes), s.stride, s.n, self._p(rows), cap, self._p(runs), 0, self._p(cur), phase,
+                                                  L, M, self._stream()), "tpl_afterstates_distinct")
+        r, d = self._distinct_result(rows, runs, phase)
+        # the device-side expansion must agree with the host helper
+        if s.n:
+            t = self.torch
+            out = t.zeros((40, s.n, 4), dtype=t.uint8, device=self.dev)
+            self._chk(self.L.tpl_expand_distinct(self._p(rows), self._p(runs), s.n, self._p(out), self._stream()), "tpl_expand_distinct")
+            from importlib import import_module
+            import tetris_piclim
+            dm = import_module(tetris_piclim.__name__ + ".distinct")
+            assert np.array_equal(out.cpu().numpy().transpose(1, 0, 2), dm.expand(r, d)), "tpl_expand_distinct != distinct.expand"
+        return r, d
+
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False):
         t = self.torch; n = s.n
         rot = self._t(np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8), np.uint8)
         loc = self._t(np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8), np.uint8)
         z = lambda shape, dt: t.zeros(shape, dtype=dt, device=self.dev)     # noqa: E731
         dl, fl, st = z(n, t.int8), z(n, t.uint8), z(n, t.int8)
-        feats, afl = z((40, n, 4), t.uint8), (None if packed else z((40, n), t.uint8))
         stats = z(8, t.int64)
         d_ep = self._t(episode, np.uint32)
-        self._chk(self.L.tpl_step_observe(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
-                                          self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), seed, env_base, 0,
-                                          self._p(feats), self._p(afl), None, L, M, self._stream()), "tpl_step_observe")
+        d_ts = self._t(tstep, np.uint32) if tstep is not None else None
+        if distinct:
+            rows, cap, runs, cur, phase = self._distinct_args(n)
+            self._chk(self.L.tpl_step_observe_distinct(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
+                                                       self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), self._p(d_ts),
+                                                       seed, env_base, 0, self._p(rows), cap, self._p(runs), 0, self._p(cur), phase, L, M,
+                                                       self._stream()), "tpl_step_observe_distinct")
+            a, b = self._distinct_result(rows, runs, phase)
+        else:
+            feats, afl = z((40, n, 4), t.uint8), (None if packed else z((40, n), t.uint8))
+            self._chk(self.L.tpl_step_observe(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
+                                              self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), self._p(d_ts), seed,
+                                              env_base, 0, self._p(feats), self._p(afl), None, L, M, self._stream()), "tpl_step_observe")
+            a, b = feats.cpu().numpy(), (None if afl is None else afl.cpu().numpy())
         episode[:] = d_ep.cpu().numpy().view(np.uint32)
-        return (dl.cpu().numpy(), fl.cpu().numpy(), st.cpu().numpy(), feats.cpu().numpy(),
-                None if afl is None else afl.cpu().numpy(), stats.cpu().numpy())
+        if tstep is not None:
+            tstep[:] = d_ts.cpu().numpy().view(np.uint32)
+        return dl.cpu().numpy(), fl.cpu().numpy(), st.cpu().numpy(), a, b, stats.cpu().numpy()
 
     def gen_pieces(self, n, count, seed, env_base, episode0=0, episode=None):
         t = self.torch

@@ -16,6 +16,36 @@ P = 42
 FLAG_TOPOUT, FLAG_WIN, FLAG_LOSE, FLAG_ALIAS, FLAG_NOPIECE = 1, 2, 4, 8, 16
 
 
+def distinct_module():
+    """the product's host helper for the distinct-placements form (tables from the library, numpy expansion)"""
+    from importlib import import_module
+    import tetris_piclim
+    return import_module(tetris_piclim.__name__ + ".distinct")
+
+
+def check_distinct(rows, runs, grid_packed, what=""):
+    """rows / runs (distinct-placements form) against the compact 40-slot grid uint8[n, 40, 4] of the same states:
+    expand(rows, runs) == grid, run lengths follow the pieces, runs do not overlap, nothing but runs and zero gaps is used."""
+    dm = distinct_module()
+    count, slot_of, canon_of = dm.tables()
+    n = len(runs)
+    piece, off = (runs >> 29).astype(np.int64), (runs & 0x1FFFFFFF).astype(np.int64)
+    cnt = count[piece].astype(np.int64)
+    nopiece = (grid_packed[:, 0, 0] >> 3) & FLAG_NOPIECE != 0
+    assert np.array_equal(piece == 7, nopiece), f"{what}: run descriptors disagree with the grid about empty queues"
+    assert (off + cnt <= len(rows)).all(), f"{what}: a run leaves the used part of rows"
+    assert np.array_equal(dm.expand(rows, runs), grid_packed), f"{what}: expand(distinct) != 40-slot grid"
+    used = np.zeros(len(rows) + 1, np.int64)
+    np.add.at(used, off, 1); np.add.at(used, off + cnt, -1)
+    cover = np.cumsum(used)[:-1]
+    assert cover.max(initial=0) <= 1, f"{what}: runs overlap"
+    assert not rows[cover == 0].any(), f"{what}: words outside every run must be zero (alignment gaps)"
+    assert int(cnt.sum()) <= len(rows) <= int(cnt.sum()) + 3 * ((n + 31) // 32) + 3
+    # no alias flag inside the runs
+    sel = cover == 1
+    assert not ((rows[sel] & 0xFF) >> 3 & FLAG_ALIAS).any(), f"{what}: alias flag in a distinct placement"
+
+
 # ---------------------------------------------------------------------------------------------
 # input generators
 # ---------------------------------------------------------------------------------------------
@@ -200,6 +230,9 @@ def case_afterstates_vs_oracle(eng, n, L, M, seed, pre_moves=3):
     pk = eng.afterstates_packed(s, L, M).reshape(n, 40, 4)            # compact form: byte 0 = dlines | flags << 3
     exp = of.copy(); exp[:, :, 0] |= (ofl << 3)
     assert np.array_equal(pk, exp)
+    rows_d, runs_d = eng.afterstates_distinct(s, L, M)                # distinct-placements form, expanded == the oracle's grid
+    check_distinct(rows_d, runs_d, exp, "afterstates_distinct")
+    assert_same(eng, s, ost, "afterstates_distinct must not modify the state")
     return of, ofl
 
 
@@ -256,6 +289,14 @@ def case_reset(eng, pool_arrays, n=1000, seed=3, env_base=1 << 20):
     m = mask.astype(bool)
     assert np.array_equal(after["rows"][~m], before["rows"][~m]) and np.array_equal(after["moves"][~m], before["moves"][~m])
     assert np.array_equal(after["rows"][m], prow[idx][m]) and not after["moves"][m].any()
+    # (3b) masked reset WITHOUT explicit indices starts a new episode for the masked envs (counter bumped before the draw)
+    episode = np.full(n, 4, np.uint32)
+    tstep = np.full(n, 9, np.uint32)
+    eng.reset(s, pool, mask=mask, mode=1, episode=episode, seed=seed, env_base=env_base, tstep=tstep)
+    after = eng.unpack(s)
+    assert np.array_equal(episode, np.where(m, 5, 4)) and np.array_equal(tstep, np.where(m, 0, 9))
+    exp = np.array([po.config_index(seed, env_base + i, 5, K) for i in range(n)])
+    assert np.array_equal(after["rows"][m], prow[exp][m]) and np.array_equal(after["rows"][~m], before["rows"][~m])
     # (4) auto-reset: only finished envs, episode counter bumped, draw keyed by the new episode
     for _ in range(5):
         eng.step(s, rng.integers(0, 4, n), rng.integers(0, 10, n), L, M)
@@ -305,23 +346,34 @@ def case_fused_step_observe(eng, pool_arrays, n=3000, steps=45, L=10, M=30, seed
     prow, ppieces, pnp = pool_arrays
     pool = eng.make_pool(prow, ppieces, pnp)
     rng = np.random.default_rng(seed)
-    a, b = eng.empty_states(n), eng.empty_states(n)
-    ep_a, ep_b = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
-    eng.reset(a, pool, episode=ep_a, seed=seed, env_base=env_base)
+    a, b, c = eng.empty_states(n), eng.empty_states(n), eng.empty_states(n)
+    ep_a, ep_b, ep_c = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    ts_a, ts_c = np.full(n, 77, np.uint32), np.full(n, 77, np.uint32)
+    eng.reset(a, pool, episode=ep_a, seed=seed, env_base=env_base, tstep=ts_a)
     eng.reset(b, pool, episode=ep_b, seed=seed, env_base=env_base)
+    eng.reset(c, pool, episode=ep_c, seed=seed, env_base=env_base, tstep=ts_c)
+    assert not ts_a.any() and not ts_c.any()                                    # every reset zeroes the action counter
+    ts_a[:] = 5; ts_c[:] = 5
+    ever_reset = np.zeros(n, bool)
     ost = c_oracle.BatchState(n)
     oep, ots, _ = c_oracle.rollout(ost, env_base, seed, L, M, prow, ppieces, pnp, 0, True)
     tot = np.zeros(8, np.int64)
     for t in range(steps):
         rot, loc = rng.integers(0, 4, n), rng.integers(0, 10, n)
-        dl, fl, st, feats, afl, stats = eng.step_observe(a, rot, loc, pool, ep_a, seed, env_base, L, M, packed=(t % 2 == 1))
+        dl, fl, st, feats, afl, stats = eng.step_observe(a, rot, loc, pool, ep_a, seed, env_base, L, M, packed=(t % 2 == 1), tstep=ts_a)
         tot += stats
+        # the same step with the afterstates in the distinct-placements form
+        dl3, fl3, st3, rows_d, runs_d, stats3 = eng.step_observe(c, rot, loc, pool, ep_c, seed, env_base, L, M, tstep=ts_c, distinct=True)
+        assert np.array_equal(dl, dl3) and np.array_equal(fl, fl3) and np.array_equal(st, st3) and np.array_equal(stats, stats3)
+        assert np.array_equal(ep_a, ep_c) and np.array_equal(ts_a, ts_c) and np.array_equal(eng.raw(a), eng.raw(c))
         dl2, fl2, st2 = eng.step(b, rot, loc, L, M)
         eng.reset(b, pool, mode=2, episode=ep_b, seed=seed, env_base=env_base)
         f2, g2 = eng.afterstates(b, L, M)
         f2 = f2.reshape(n, 40, 4).transpose(1, 0, 2).copy(); g2 = g2.reshape(n, 40).T
         assert np.array_equal(dl, dl2) and np.array_equal(fl, fl2) and np.array_equal(st, st2)
         assert np.array_equal(ep_a, ep_b) and np.array_equal(eng.raw(a), eng.raw(b))
+        grid = f2.copy(); grid[:, :, 0] |= (g2 << 3)
+        check_distinct(rows_d, runs_d, np.ascontiguousarray(grid.transpose(1, 0, 2)), f"fused step {t}")
         if afl is None:
             f2[:, :, 0] |= (g2 << 3)
         else:
@@ -330,6 +382,8 @@ def case_fused_step_observe(eng, pool_arrays, n=3000, steps=45, L=10, M=30, seed
         odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
         assert np.array_equal(dl, odl) and np.array_equal(st, ost.state)
         done = np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]
+        ever_reset[done] = True
+        assert np.array_equal(ts_a, np.where(ever_reset, 0, 5))                  # auto-reset zeroes tstep, nothing else touches it
         for i in done:
             oep[i] += 1
             k = po.config_index(seed, env_base + int(i), int(oep[i]), len(prow))

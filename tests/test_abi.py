@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(tp):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/tetris_piclim.h but not exported"
     assert sorted(tp._lib.ALL_SYMBOLS) == syms, "python binding table and header disagree"
-    assert lib.tpl_abi_version() == 1
+    assert lib.tpl_abi_version() == 2
 
 
 def test_config_generator_library_exports_its_header(tp):

@@ -25,17 +25,25 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["metric"] == "afterstates/sec" and d["unit"] == "afterstates/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["config"]["envs_total"] == 1 << 20 and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "game", "tetris.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "reference_sample" in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 @pytest.mark.gpu
 def test_b200_arm_line(gpu):
-    d = _run(["--steps", "4", "--warmup", "3"], 900)
-    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    d = _run(["--steps", "4", "--warmup", "3", "--no-dqn"], 900)
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "e2e_40slot", "distinct_form", "collective_us", "pcie"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 4 and d["gpu_launches"] == 4 and d["scaling"] == "weak" and d["vs_baseline"] is None
     rf = d["roofline"]
-    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 2 << 20 and d["e2e"]["d2h_bytes_per_step"] == 163 << 20 and 0 < d["e2e"]["value"] < d["value"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["traffic"] is None or rf["traffic"] > 0          # null unless profiles/r02_ncu_current.json matches this build
+    n = 1 << 20
+    assert d["e2e_40slot"]["h2d_bytes_per_step"] == 2 * n and d["e2e_40slot"]["d2h_bytes_per_step"] == 163 * n
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * n and 90 * n < d["e2e"]["d2h_bytes_per_step"] < 110 * n
+    assert 0 < d["e2e_40slot"]["value"] < d["e2e"]["value"] < d["value"]
+    assert 22 < d["distinct_form"]["words_per_env"] < 24.5
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"] == dict(d["config"]) and "model" not in d["config"]

@@ -179,6 +179,116 @@ def test_host_api_vs_oracle(tp, carve_pool):
     env.close()
 
 
+def _oracle_autoreset(ost, oep, seed, env_base, pool):
+    for i in np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]:
+        oep[i] += 1
+        k = po.config_index(seed, env_base + int(i), int(oep[i]), pool.K)
+        ost.rows[i] = pool.rows[k]; ost.pieces[i] = 0; ost.pieces[i, :pool.pieces.shape[1]] = pool.pieces[k]
+        ost.npieces[i] = pool.npieces[k]
+        ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
+
+
+@pytest.mark.parametrize("n,chunks", [(3000, None), (200_000, None), (70_001, "3")])
+def test_host_api_pipelined_and_distinct(tp, carve_pool, n, chunks, monkeypatch):
+    """tpl_env_step_observe (40-slot forms) and tpl_env_step_observe_distinct through HOST buffers, with the batch cut into
+    chunks (200 000 envs -> 3 chunks; 70 001 envs forced into 3 ragged chunks): every chunk's results land at the right
+    place of the caller's arrays, and the distinct form expands to the oracle's grid."""
+    from tests import parity_cases as pc
+    if chunks:
+        monkeypatch.setenv("TPL_ENV_CHUNKS", chunks)
+    L, M, seed, base = 10, 30, 41, 1 << 35
+    envs = [tp.HostBatchedTetris(n, L, M, seed=seed, env_base=base, config_pool=carve_pool) for _ in range(2)]
+    assert envs[0].chunks() == (1 if n < 131072 and not chunks else 3)
+    for e in envs:
+        e.reset()
+    ost = c_oracle.BatchState(n)
+    oep, _, _ = c_oracle.rollout(ost, base, seed, L, M, carve_pool.rows, carve_pool.pieces, carve_pool.npieces, 0, True)
+    rng = np.random.default_rng(3)
+    cap = envs[1].distinct_capacity()
+    pin = {k: tp.PinnedArray(s, d) for k, (s, d) in dict(rot=((n,), np.uint8), loc=((n,), np.uint8), dl=((n,), np.int8),
+           fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8), afl=((40, n), np.uint8),
+           dl2=((n,), np.int8), fl2=((n,), np.uint8), st2=((n,), np.int8), rows=((cap,), np.uint32), runs=((n,), np.uint32)).items()}
+    for t in range(6):
+        rot, loc = rng.integers(0, 4, n), rng.integers(0, 10, n)
+        pin["rot"].array[:] = rot; pin["loc"].array[:] = loc
+        packed = t % 2 == 0
+        envs[0].step_observe(*[pin[k].array for k in ("rot", "loc", "dl", "fl", "st", "feats")], None if packed else pin["afl"].array)
+        pin["rows"].array[:] = 0xFFFFFFFF
+        words = envs[1].step_observe_distinct(*[pin[k].array for k in ("rot", "loc", "dl2", "fl2", "st2", "rows", "runs")])
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        for a, b in (("dl", "dl2"), ("fl", "fl2"), ("st", "st2")):
+            assert np.array_equal(pin[a].array, pin[b].array)
+        assert np.array_equal(pin["dl"].array, odl) and np.array_equal(pin["st"].array, ost.state)
+        _oracle_autoreset(ost, oep, seed, base, carve_pool)
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=8)
+        grid = of.copy(); grid[:, :, 0] |= ofl << 3
+        if packed:
+            assert np.array_equal(pin["feats"].array.transpose(1, 0, 2), grid)
+        else:
+            assert np.array_equal(pin["feats"].array.transpose(1, 0, 2), of) and np.array_equal(pin["afl"].array.T, ofl)
+        dm = pc.distinct_module()
+        runs = pin["runs"].array
+        assert np.array_equal(dm.expand(pin["rows"].array, runs), grid)
+        cnt = dm.tables()[0][runs >> 29].astype(np.int64)
+        assert cnt.sum() <= words <= cnt.sum() + 3 * ((n + 31) // 32 + 8)          # only the used words crossed PCIe
+        assert words < 0.7 * 40 * n
+    for e in envs:
+        f = e.fields()
+        assert np.array_equal(f["rows"], ost.rows) and np.array_equal(f["moves"], ost.moves)
+        e.close()
+
+
+def test_batched_distinct_forms(tp, carve_pool):
+    """BatchedTetris.afterstates_distinct / step_observe_distinct / expand_distinct and the torch gather helper"""
+    import torch
+    from tests import parity_cases as pc
+    n, L, M, seed = 50_000, 10, 30, 5
+    env = tp.BatchedTetris(n, L, M, seed=seed, config_pool=carve_pool)
+    env.reset()
+    ost = c_oracle.BatchState(n)
+    oep, _, _ = c_oracle.rollout(ost, 0, seed, L, M, carve_pool.rows, carve_pool.pieces, carve_pool.npieces, 0, True)
+    rng = np.random.default_rng(4)
+    dm = pc.distinct_module()
+    for t in range(5):
+        if t == 0:
+            rows, runs, used = env.afterstates_distinct()
+        else:
+            rot, loc = rng.integers(0, 4, n).astype(np.uint8), rng.integers(0, 10, n).astype(np.uint8)
+            dl, fl, st, rows, runs, used = env.step_observe_distinct(torch.from_numpy(rot).cuda(), torch.from_numpy(loc).cuda())
+            odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+            assert np.array_equal(dl.cpu().numpy(), odl) and np.array_equal(st.cpu().numpy(), ost.state)
+            _oracle_autoreset(ost, oep, seed, 0, carve_pool)
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=8)
+        grid = of.copy(); grid[:, :, 0] |= ofl << 3
+        r = rows.cpu().numpy().view(np.uint32)[:int(used)]
+        d = runs.cpu().numpy().view(np.uint32)
+        pc.check_distinct(r, d, grid, f"step {t}")
+        assert np.array_equal(env.expand_distinct(rows, runs).cpu().numpy().transpose(1, 0, 2), grid)
+        idx, valid, slot = dm.gather_index(runs)
+        w = rows.view(torch.uint8).view(-1, 4)[idx]                                    # [n, 34, 4] padded placements
+        g = torch.from_numpy(grid).cuda()
+        pick = g[torch.arange(n, device="cuda")[:, None], slot.clamp(max=39)]          # the grid at each placement's (rot, loc)
+        assert bool((w[valid] == pick[valid]).all())
+        assert int(valid.sum()) == int(dm.tables()[0][d >> 29].sum())
+    f = env.fields()
+    assert np.array_equal(f["rows"].cpu().numpy(), ost.rows)
+
+
+def test_env_on_non_current_device(tp, carve_pool):
+    """every C call runs with the env's device current: drive an env while another device is current"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 4096
+    env = tp.BatchedTetris(n, 10, 30, device="cuda:1", seed=1, config_pool=carve_pool)
+    ref = tp.BatchedTetris(n, 10, 30, device="cuda:0", seed=1, config_pool=carve_pool)
+    torch.cuda.set_device(0)
+    for e in (env, ref):
+        e.reset(); e.rollout_random(5)
+    a, b = env.afterstates(packed=True)[0], ref.afterstates(packed=True)[0]
+    assert torch.equal(a.cpu(), b.cpu())
+
+
 def test_error_codes(tp):
     import ctypes
     L = tp._lib.lib()
