@@ -186,6 +186,30 @@ int tpl_rollout_greedy(void *state, int64_t plane_stride, int n, const void *poo
                        uint64_t seed, uint64_t env_base, int gen_count, int L, int M, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * value net for ranking afterstates: the reference's layer shape model/model.py:9-20 as 4 -> 128 -> 128 -> 128
+ * -> 128 -> 1, inference only, bf16 operands with fp32 accumulation on the tensor cores (tcgen05), weights and activations
+ * on chip.  Training stays in PyTorch; these calls only serve the rollout's action selection.  Device pointers.
+ * ------------------------------------------------------------------------------------------------- */
+#define TPL_VALUE_BLOB_BYTES 104480
+/* fp32 parameters in PyTorch layout (weight [out][in]: w1 [128][4], w2..w4 [128][128], w5 [1][128]; biases [128] / [1]) ->
+ * the packed bf16 blob (TPL_VALUE_BLOB_BYTES, 16-byte aligned) tpl_value_rows reads.  scale4_host: HOST float[4], the factors the
+ * four u8 features (rows cleared, holes, bumpiness, aggregate height) are multiplied by before the first layer. */
+int tpl_value_pack(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3, const float *b3,
+                   const float *w4, const float *b4, const float *w5, const float *b5, const float *scale4_host, void *blob,
+                   void *stream);
+/* values[r] = V(rows[r]) for every r < min(*count, nrows_max) (count == NULL: r < nrows_max): rows are feature words in the
+ * distinct-placements form (byte 0 & 7 = rows cleared, bytes 1-3 = holes, bumpiness, aggregate height); count is typically
+ * cursor2[phase] of the tpl_*_distinct call that wrote them, read on the device -- no host synchronisation. */
+int tpl_value_rows(const uint32_t *rows, const uint32_t *count, int64_t nrows_max, const void *blob, float *values, void *stream);
+/* Per env, over its run of distinct placements: q = rows cleared + reward_win / reward_lose on a winning / losing (or
+ * topping-out) placement + gamma * values; arg-max (lowest placement on ties), replaced with probability eps by a uniformly
+ * random placement (counter RNG, stream 3, keyed by (seed, env_base + i, step)).  Outputs: rot / loc u8[n] (the action for
+ * tpl_step*), chosen u32[n] (optional: the chosen placement's feature word), chosen_q f32[n] (optional: the arg-max q). */
+int tpl_select_action(const uint32_t *rows, const uint32_t *runs, const float *values, int n, float gamma, float reward_win,
+                      float reward_lose, float eps, uint64_t seed, uint64_t env_base, uint32_t step, uint8_t *rot, uint8_t *loc,
+                      uint32_t *chosen, float *chosen_q, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * host-buffer API (handle owns device memory; every array is a HOST pointer)
  * ------------------------------------------------------------------------------------------------- */
 typedef struct tpl_env tpl_env;

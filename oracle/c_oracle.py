@@ -143,4 +143,19 @@ def rollout(st: BatchState, env_base: int, seed: int, L: int, M: int, pool_rows,
     return episode, tstep, stats
 
 
+def reset_done(st: BatchState, env_base: int, seed: int, pool_rows, pool_pieces, pool_np, episode, tstep=None) -> int:
+    """Auto-reset of the envs whose episode has ended (TPL_RESET_DONE): episode bumped, config drawn by the counter RNG."""
+    pool_rows = np.ascontiguousarray(pool_rows, np.uint16)
+    K = pool_rows.shape[0]
+    pp = np.zeros((K, st.P), np.uint8)
+    pool_pieces = np.asarray(pool_pieces, np.uint8)
+    pp[:, :pool_pieces.shape[1]] = pool_pieces
+    pool_np = np.ascontiguousarray(pool_np, np.uint8)
+    return int(lib().orc_reset_done(ctypes.c_int(st.n), ctypes.c_uint64(env_base), ctypes.c_uint64(seed), _p(pool_rows, ctypes.c_uint16),
+                                    _p(pp, ctypes.c_uint8), ctypes.c_int(st.P), _p(pool_np, ctypes.c_uint8), ctypes.c_int(K),
+                                    _p(st.rows, ctypes.c_uint16), _p(st.pieces, ctypes.c_uint8), _p(st.npieces, ctypes.c_uint8),
+                                    _p(st.head, ctypes.c_uint8), _p(st.lines, ctypes.c_int32), _p(st.moves, ctypes.c_int32),
+                                    _p(st.state, ctypes.c_int8), _p(episode, ctypes.c_uint32), _p(tstep, ctypes.c_uint32)))
+
+
 rollout_random = rollout

@@ -351,4 +351,20 @@ void orc_rollout(int n, uint64_t env_base, uint64_t seed, int L, int M,
     free(jb);
 }
 
+/* Auto-reset (the TPL_RESET_DONE semantics the fused step applies after the move): every env that left RUNNING or ran out of
+ * pieces starts its next episode -- counter bumped, then the same config draw as the rollouts.  Returns the number reset. */
+int orc_reset_done(int n, uint64_t env_base, uint64_t seed, const uint16_t *pool_rows, const uint8_t *pool_pieces, int P,
+                   const uint8_t *pool_np, int K, uint16_t *rows, uint8_t *pieces, uint8_t *npieces, uint8_t *head,
+                   int32_t *lines, int32_t *moves, int8_t *state, uint32_t *episode, uint32_t *tstep) {
+    ro_job j; memset(&j, 0, sizeof(j));
+    j.env_base = env_base; j.seed = seed; j.pool_rows = pool_rows; j.pool_pieces = pool_pieces; j.P = P; j.pool_np = pool_np; j.K = K;
+    j.rows = rows; j.pieces = pieces; j.npieces = npieces; j.head = head; j.lines = lines; j.moves = moves; j.state = state;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i)
+        if (state[i] != 0 || head[i] >= npieces[i]) {
+            episode[i] += 1; if (tstep) tstep[i] = 0; install(&j, i, episode[i]); ++cnt;
+        }
+    return cnt;
+}
+
 int orc_abi_version(void) { return 1; }

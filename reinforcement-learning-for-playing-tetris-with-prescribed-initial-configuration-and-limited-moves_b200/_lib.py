@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int64, c_longlong, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libtetris_piclim_sm100.so")      # short in-tree path, see build.py
@@ -26,6 +26,9 @@ DEVICE_API = {
     "step_observe_distinct": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, c_int, P, P, c_uint64, c_uint64, c_int, P, c_int64, P, c_uint32,
                                       P, c_int, c_int, c_int, P]),
     "expand_distinct": (c_int, [P, P, c_int, P, P]),
+    "value_pack": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "value_rows": (c_int, [P, P, c_int64, P, P, P]),
+    "select_action": (c_int, [P, P, P, c_int, c_float, c_float, c_float, c_float, c_uint64, c_uint64, c_uint32, P, P, P, P, P]),
     "gen_pieces": (c_int, [P, c_int, c_int, c_uint64, c_uint64, P, c_uint32, P]),
     "rollout_random": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int, c_int, c_int, P]),
     "rollout_greedy": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, P, c_uint64, c_uint64, c_int, c_int, c_int, P]),

@@ -30,7 +30,11 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class BatchedTetris:
     """N envs with shared (L, M).  ``env_base`` is the global id of env 0 (multi-GPU sharding keeps the RNG
-    streams a function of the *global* env id, so results do not depend on the number of ranks)."""
+    streams a function of the *global* env id, so results do not depend on the number of ranks).
+    ``gen_pieces`` > 0: every reset replaces the pool's piece list by that many pieces of the counter-based 7-bag sequence
+    of (seed, env, episode); it may exceed the 42 pieces the env record holds (e.g. M + 1 = 61): the kernels that know the RNG
+    keys (``step_observe*``, the rollouts, ``reset(done_only=True)``) refill the queue when it runs dry mid-episode.  After a
+    plain ``move`` call ``reset(done_only=True)`` to get the refill (``move`` alone reports FLAG_NOPIECE on an empty queue)."""
 
     def __init__(self, num_envs: int, L: int, M: int, device="cuda", seed: int = 0,
                  config_pool: Optional[ConfigPool] = None, env_base: int = 0, gen_pieces: int = 0):
@@ -38,6 +42,8 @@ class BatchedTetris:
             raise ValueError("num_envs must be positive")
         if not (0 <= L <= 65535 and 0 <= M <= 65535):
             raise ValueError("L and M must fit 16 bits")
+        if not 0 <= int(gen_pieces) <= 42 * 256:
+            raise ValueError("gen_pieces must be in 0..10752")
         self._L = _lib.lib()                                    # raises if the CUDA library is missing
         self.device = torch.device(device)
         if self.device.type != "cuda":

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(os.path.dirname(HERE), "lib")
 LIB_NAME = "libtetris_piclim_sm100.so"
 LIB_PATH = os.path.join(LIB_DIR, LIB_NAME)
-SOURCES = ["piclim_kernels.cu", "piclim_host_api.cu"]
+SOURCES = ["piclim_kernels.cu", "piclim_host_api.cu", "piclim_value.cu"]
 HEADERS = ["piclim_core.cuh", "piclim_env.cuh", os.path.join("..", "..", "include", "tetris_piclim.h")]
 
 NVCC_FLAGS = [

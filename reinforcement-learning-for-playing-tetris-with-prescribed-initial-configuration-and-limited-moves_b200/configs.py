@@ -79,16 +79,22 @@ def bags_from_words(u) -> np.ndarray:
     return flat.reshape(u.shape + (7,))
 
 
+GEN_MAX = MAX_PIECES * 256       # longest generated sequence (the kernels refill the 42-piece queue block by block)
+
+
 def gen_pieces(seed: int, env_ids, episode, count: int) -> np.ndarray:
-    """Counter-based 7-bag sequences uint8[n, count] (count <= 42): concatenated bags, truncated, the contract of
-    RandomPieceGenerator.get_random_sequence (``game/tetris.py:95-102``)."""
-    if not 0 <= count <= MAX_PIECES:
-        raise ValueError("count must be in 0..42")
+    """Counter-based 7-bag sequences uint8[n, count]: concatenated bags, truncated, the contract of
+    RandomPieceGenerator.get_random_sequence (``game/tetris.py:95-102``).  Bag g comes from word g & 3 of Philox call g >> 2."""
+    if not 0 <= count <= GEN_MAX:
+        raise ValueError(f"count must be in 0..{GEN_MAX}")
     env_ids = np.asarray(env_ids, np.uint64).reshape(-1)
-    w0 = rng_words(seed, env_ids, episode, STREAM_PIECES, 0)
-    w1 = rng_words(seed, env_ids, episode, STREAM_PIECES, 1)
-    words = np.stack([w0[0], w0[1], w0[2], w0[3], w1[0], w1[1]], axis=1)      # [n, 6]
-    return bags_from_words(words).reshape(len(env_ids), 42)[:, :count].astype(np.uint8)
+    nbags = max((count + 6) // 7, 1)
+    words = []
+    for call in range((nbags + 3) // 4):
+        w = rng_words(seed, env_ids, episode, STREAM_PIECES, call)
+        words += [w[0], w[1], w[2], w[3]]
+    words = np.stack(words[:nbags], axis=1)                                     # [n, nbags]
+    return bags_from_words(words).reshape(len(env_ids), 7 * nbags)[:, :count].astype(np.uint8)
 
 
 def synthetic_pool(K: int, seed: int = 0, M: int = 30, max_height: int = 12, fill_byte: int = 154) -> ConfigPool:
@@ -96,7 +102,8 @@ def synthetic_pool(K: int, seed: int = 0, M: int = 30, max_height: int = 12, fil
     P(bit) = fill_byte/256 (154/256 = 0.6016), resampled while the row is empty or full; rows above empty;
     pieces = M+1 pieces of the counter-based 7-bag stream of (seed, config id, episode 0xB0A2D)."""
     if M + 1 > MAX_PIECES:
-        raise ValueError("M + 1 pieces must fit the 42-piece queue")
+        raise ValueError("a pool stores explicit piece lists of at most 42 pieces (M <= 41); for longer episodes take the boards from "
+                         "any pool and let the kernels generate the pieces: BatchedTetris(..., gen_pieces=M + 1)")
     ids = np.arange(K, dtype=np.uint64)
     hw = rng_words(seed, ids, 0, STREAM_BOARD, 0x0FFFFFFF)[0]
     H = ((hw * np.uint64(max_height + 1)) >> _S32).astype(np.int64)
@@ -183,7 +190,8 @@ def carve_pool(K: int, L: int, M: int, seed0: int = 0, threads: Optional[int] = 
     import os
     from . import build as _build
     if M + 1 > MAX_PIECES:
-        raise ValueError("M + 1 pieces must fit the 42-piece queue")
+        raise ValueError("a pool stores explicit piece lists of at most 42 pieces (M <= 41); for longer episodes take the boards from "
+                         "any pool and let the kernels generate the pieces: BatchedTetris(..., gen_pieces=M + 1)")
     lib = ctypes.CDLL(_build.build_carve())
     lib.carve_generate.restype = ctypes.c_int
     lib.carve_generate.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 2 +         [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int]
@@ -234,7 +242,8 @@ def forward_pool(L: int, M: int, start: int = 0, end: int = 100, initial_height_
     point is drawn from Python's GLOBAL ``random`` stream, one draw per winnable game in seed order."""
     import random
     if M + 1 > MAX_PIECES:
-        raise ValueError("M + 1 pieces must fit the 42-piece queue")
+        raise ValueError("a pool stores explicit piece lists of at most 42 pieces (M <= 41); for longer episodes take the boards from "
+                         "any pool and let the kernels generate the pieces: BatchedTetris(..., gen_pieces=M + 1)")
     g = forward_games(L, M, start, end - start, initial_height_max, max_attempts, threads)
     keep = np.flatnonzero(g["solvable"])
     pieces = np.zeros((len(keep), MAX_PIECES), np.uint8)

@@ -136,6 +136,7 @@ struct Env {
     uint32_t col[COLS];
     uint32_t q[4];          // piece queue, 3 bits per piece
     uint32_t lines, moves, state, head, npieces;
+    uint32_t qblock;        // generated queues longer than 42 pieces: which 42-piece block of the episode's sequence q holds
 };
 
 __device__ __forceinline__ uint4 ldg_plain(const uint4 *p) { return *p; }
@@ -146,11 +147,11 @@ __device__ __forceinline__ void unpack_env(const uint4 &a, const uint4 &b, const
     e.col[8] = c.x; e.col[9] = c.y; e.q[0] = c.z; e.q[1] = c.w;
     e.q[2] = d.x; e.q[3] = d.y;
     e.lines = d.z & 0xFFFFu; e.moves = d.z >> 16;
-    e.state = d.w & 0xFFu; e.head = (d.w >> 8) & 0xFFu; e.npieces = (d.w >> 16) & 0xFFu;
+    e.state = d.w & 0xFFu; e.head = (d.w >> 8) & 0xFFu; e.npieces = (d.w >> 16) & 0xFFu; e.qblock = d.w >> 24;
 }
 __device__ __forceinline__ uint4 pack_meta(const Env &e) {
     return make_uint4(e.q[2], e.q[3], (e.lines & 0xFFFFu) | (e.moves << 16),
-                      (e.state & 0xFFu) | ((e.head & 0xFFu) << 8) | ((e.npieces & 0xFFu) << 16));
+                      (e.state & 0xFFu) | ((e.head & 0xFFu) << 8) | ((e.npieces & 0xFFu) << 16) | (e.qblock << 24));
 }
 
 // state planes: chunk j of env i at st[j * stride + i]
@@ -354,12 +355,16 @@ __device__ __forceinline__ uint32_t bag_from_word(uint32_t u) {
     return perm;
 }
 
-// the first `count` (<= 42) pieces of episode `episode` of env `env`, packed 3 bits each
-__device__ __forceinline__ void gen_queue(uint64_t seed, uint64_t env, uint32_t episode, int count, uint32_t (&q)[4]) {
+// pieces [42 * block, 42 * block + count) (count <= 42) of episode `episode` of env `env`, packed 3 bits each.  The episode's
+// sequence is a concatenation of 7-bags; bag g comes from word (g & 3) of Philox call (g >> 2) of the piece stream, so the six
+// bags of a block are six consecutive words of two calls, starting at word 0 or 2 (block 0: calls 0 and 1, words 0..5).
+__device__ __forceinline__ void gen_queue(uint64_t seed, uint64_t env, uint32_t episode, int count, uint32_t (&q)[4], uint32_t block = 0) {
     uint64_t lo = 0, hi = 0;
-    uint4 w0 = rng_words(seed, env, episode, STREAM_PIECES, 0);
-    uint4 w1 = rng_words(seed, env, episode, STREAM_PIECES, 1);
-    const uint32_t ws[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+    const uint32_t g0 = 6u * block, c0 = g0 >> 2;
+    const bool odd = (g0 & 2u) != 0u;
+    uint4 w0 = rng_words(seed, env, episode, STREAM_PIECES, c0);
+    uint4 w1 = rng_words(seed, env, episode, STREAM_PIECES, c0 + 1u);
+    const uint32_t ws[6] = {odd ? w0.z : w0.x, odd ? w0.w : w0.y, odd ? w1.x : w0.z, odd ? w1.y : w0.w, odd ? w1.z : w1.x, odd ? w1.w : w1.y};
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
         const uint64_t perm = bag_from_word(ws[b]);
@@ -371,6 +376,23 @@ __device__ __forceinline__ void gen_queue(uint64_t seed, uint64_t env, uint32_t 
     if (bits < 64) { lo &= (1ull << bits) - 1ull; hi = 0; }
     else if (bits < 128) hi &= (1ull << (bits - 64)) - 1ull;
     q[0] = (uint32_t)lo; q[1] = (uint32_t)(lo >> 32); q[2] = (uint32_t)hi; q[3] = (uint32_t)(hi >> 32);
+}
+
+constexpr int QUEUE_PIECES = 42;                 // pieces the 128-bit queue holds
+constexpr int GEN_MAX = QUEUE_PIECES * 256;      // longest generated sequence (the block number is one byte of the record)
+
+// Generated sequences longer than the queue (gen_total > 42, i.e. M > 41): when the queue runs dry mid-episode, the next
+// 42-piece block of the same counter-based sequence is generated in place (RandomPieceGenerator.get_random_sequence yields
+// sequences of ANY length, game/tetris.py:95-102).  True if the env was running on an empty queue and got new pieces.
+__device__ __forceinline__ bool refill_queue(Env &e, uint64_t seed, uint64_t env, uint32_t episode, int gen_total) {
+    if (gen_total <= QUEUE_PIECES || e.state != S_RUNNING || e.head < e.npieces) return false;
+    const int done = (int)(e.qblock + 1u) * QUEUE_PIECES;
+    if (done >= gen_total) return false;
+    e.qblock += 1u;
+    const int count = min(QUEUE_PIECES, gen_total - done);
+    gen_queue(seed, env, episode, count, e.q, e.qblock);
+    e.head = 0; e.npieces = (uint32_t)count;
+    return true;
 }
 
 __device__ __forceinline__ uint32_t config_index(uint64_t seed, uint64_t env, uint32_t episode, int K) {

@@ -4,10 +4,6 @@
 #pragma once
 #include "piclim_core.cuh"
 
-#ifndef TPL_PACKED_Y
-#define TPL_PACKED_Y 0              // tuning knob (see TPL_PAIR in afterstates_env_impl)
-#endif
-
 namespace tpl {
 
 // ---------------------------------------------------------------------------------------------
@@ -48,8 +44,11 @@ __device__ __forceinline__ void install_config(Env &e, const uint4 *__restrict__
                                                uint64_t env, uint32_t episode, int gen_count) {
     const uint4 a = pool[4 * (size_t)k], b = pool[4 * (size_t)k + 1], c = pool[4 * (size_t)k + 2], d = pool[4 * (size_t)k + 3];
     unpack_env(a, b, c, d, e);
-    e.lines = 0; e.moves = 0; e.state = S_RUNNING; e.head = 0;
-    if (gen_count > 0) { gen_queue(seed, env, episode, gen_count, e.q); e.npieces = (uint32_t)gen_count; }
+    e.lines = 0; e.moves = 0; e.state = S_RUNNING; e.head = 0; e.qblock = 0;
+    if (gen_count > 0) {                      // (more than 42: the first block now, the rest by refill_queue as the episode goes on)
+        const int first = gen_count < QUEUE_PIECES ? gen_count : QUEUE_PIECES;
+        gen_queue(seed, env, episode, first, e.q); e.npieces = (uint32_t)first;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -108,8 +107,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           uint32_t flN, uint32_t flT, int w,
                                           int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
                                           uint32_t TO4, uint32_t cover, uint32_t hm, int thr, uint32_t one,
-                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp,
-                                          int y_packed = 0) {
+                                          uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
     // Distinct-placements form: alias slots are not stored at all, so a column that no distinct placement of ANY piece reaches in
     // this rotation is skipped outright -- rotation 0: column 9; rotation 2: columns 8 and 9 (the only two-wide shape there is O,
     // whose rotation 2 is an alias); rotation 3: column 9 (the one-wide vertical I is an alias there).  36 of 40 slots are left.
@@ -132,9 +130,6 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     // the value 1 from a kernel parameter -- opaque to ptxas, which would otherwise fuse each sum into an ALU-pipe
     // VIADDMNMX -- and the four-way max is VIMNMX3 + VIMNMX: 2 ALU-pipe instructions instead of 3.
     int y;
-#if TPL_PACKED_Y
-    y = y_packed;                                      // (hard drops of columns C and C + 1 taken together as s16x2, see TPL_PAIR)
-#else
     if (C <= 6) {
         const int t0 = (int)mad_fma_pipe((uint32_t)H[C], one, (uint32_t)nb0), t1 = (int)mad_fma_pipe((uint32_t)H[C + 1], one, (uint32_t)nb1);
         const int t2 = (int)mad_fma_pipe((uint32_t)H[C + 2], one, (uint32_t)nb2), t3 = (int)mad_fma_pipe((uint32_t)H[C + 3], one, (uint32_t)nb3);
@@ -142,7 +137,6 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     } else {
         y = max(max(H[C] + nb0, H[C + 1] + nb1), __viaddmax_s32(H[C + 3], nb3, H[C + 2] + nb2));
     }
-#endif
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
     // the piece lands on empty cells, so `column | piece image` is `column + piece image`: one IMAD per window column
@@ -271,11 +265,6 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     for (int k = 0; k < COLS; ++k) { col[k] = e.col[k]; H[k] = col_height(col[k]); cells += __popc(col[k]); }
 #pragma unroll
     for (int k = COLS; k < 14; ++k) { col[k] = COL_FULL; H[k] = 0; }
-#if TPL_PACKED_Y
-    uint32_t HP[13];                                 // HP[c] = H[c] | H[c + 1] << 16
-#pragma unroll
-    for (int k = 0; k < 13; ++k) HP[k] = (uint32_t)H[k] | ((uint32_t)H[k + 1] << 16);
-#endif
     const uint32_t HB0 = H[0] | (H[1] << 8) | (H[2] << 16) | (H[3] << 24);
     const uint32_t HB1 = H[4] | (H[5] << 8) | (H[6] << 16) | (H[7] << 24);
     const uint32_t HB2 = H[8] | (H[9] << 8);
@@ -330,21 +319,9 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         uint32_t word = 0, fl = 0, pmask = 0, nsmask = 0; bool pend = false;
         if constexpr (Sink::RAGGED) sink.begin_rotation_ragged(canon, orient_rot_base(tab[(piece * 4 + r) * 2 + 1]));
         else if constexpr (Sink::PACKED) sink.begin_rotation(r);
-#define TPL_SLOT(C, Y) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
-                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp, Y);
-#if TPL_PACKED_Y
-        // Two adjacent columns share one packed hard drop: halves (H[c], H[c+1]) + (nb_j, nb_j) through four s16x2 add-max
-        // instructions (VIADDMNMX.S16x2) give y(c) | y(c + 1) << 16 -- 2 instructions per slot instead of 4 adds + 2 max.
-        const uint32_t NB0 = ((uint32_t)nb0 & 0xFFFFu) * 0x10001u, NB1 = ((uint32_t)nb1 & 0xFFFFu) * 0x10001u,
-                       NB2 = ((uint32_t)nb2 & 0xFFFFu) * 0x10001u, NB3 = ((uint32_t)nb3 & 0xFFFFu) * 0x10001u;
-#define TPL_PAIR(C) { uint32_t y2 = __viaddmax_s16x2(HP[C], NB0, 0x80008000u); y2 = __viaddmax_s16x2(HP[C + 1], NB1, y2); \
-                      y2 = __viaddmax_s16x2(HP[C + 2], NB2, y2); y2 = __viaddmax_s16x2(HP[C + 3], NB3, y2); \
-                      TPL_SLOT(C, (int)(y2 & 0xFFFFu)) TPL_SLOT(C + 1, (int)(y2 >> 16)) }      /* y >= 0 wherever the shape fits */
-        TPL_PAIR(0) TPL_PAIR(2) TPL_PAIR(4) TPL_PAIR(6) TPL_PAIR(8)
-#undef TPL_PAIR
-#else
-        TPL_SLOT(0, 0) TPL_SLOT(1, 0) TPL_SLOT(2, 0) TPL_SLOT(3, 0) TPL_SLOT(4, 0) TPL_SLOT(5, 0) TPL_SLOT(6, 0) TPL_SLOT(7, 0) TPL_SLOT(8, 0) TPL_SLOT(9, 0)
-#endif
+#define TPL_SLOT(C) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
+                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
+        TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         if (canon) pending |= (unsigned long long)pmask << (10 * r);
         if constexpr (UNIFORM) notstored |= (unsigned long long)nsmask << (10 * r);
@@ -389,7 +366,7 @@ __device__ __forceinline__ void afterstates_env(const Env &e, const uint4 *tab, 
 __device__ __forceinline__ void rollout_random_step(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
                                                     uint32_t *scr, int ss, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
                                                     int gen_count, int L, int M) {
-    if (e.state != S_RUNNING || e.head >= e.npieces) {
+    if (!refill_queue(e, seed, env, ep, gen_count) && (e.state != S_RUNNING || e.head >= e.npieces)) {
         ep += 1; t = 0; acc[7] += 1;
         install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
     }
@@ -452,7 +429,7 @@ template <bool W16 = false>
 __device__ __forceinline__ void rollout_greedy_step(Env &e, uint32_t &ep, uint32_t &t, uint32_t (&acc)[8], const uint4 *tab,
                                                     uint32_t *scr, int ss, const uint4 *__restrict__ pool, int K, uint64_t seed, uint64_t env,
                                                     int gen_count, int L, int M, const GreedyWeights &gw) {
-    if (e.state != S_RUNNING || e.head >= e.npieces) {
+    if (!refill_queue(e, seed, env, ep, gen_count) && (e.state != S_RUNNING || e.head >= e.npieces)) {
         ep += 1; t = 0; acc[7] += 1;
         install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
     }

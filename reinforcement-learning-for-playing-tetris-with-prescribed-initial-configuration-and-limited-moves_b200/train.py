@@ -7,8 +7,15 @@ exponentially decaying epsilon-greedy, Huber loss, soft target update with TAU).
 
 Afterstate formulation: the action value of placing the current piece at slot (rot, loc) is
 ``r(slot) + GAMMA * V(afterstate(slot))``; ``V`` is ``ValueNet`` on the four features the env kernel emits.
-Everything stays on the GPU: env state, the 40-slot enumeration (``tpl_afterstates``), the chosen move
-(``tpl_step``), auto-reset (``tpl_reset_from_pool``), the replay memory and the network.
+Everything stays on the GPU: env state, the afterstate enumeration, the chosen move, auto-reset (one fused kernel,
+``tpl_step_observe*``), the replay memory and the network.
+
+Two rollout paths share the optimiser half:
+* ``value_kernel=True`` (default): the env reports only the DISTINCT placements (``tpl_step_observe_distinct``: 23 instead of
+  40 rows per env), the ranking forward pass over them is the fused tensor-core kernel (``tpl_value_rows``, weights and
+  activations on chip) and the epsilon-greedy arg-max is ``tpl_select_action`` -- three launches per step, no [40 N, 128]
+  activations in HBM.  The network, the loss and the optimiser are plain PyTorch.
+* ``value_kernel=False``: the 40-slot form with the forward pass in PyTorch (``ValueNet.rank_bf16``), kept as the reference.
 """
 from __future__ import annotations
 
@@ -21,8 +28,10 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
+from . import distinct as _distinct
 from .batched import FLAG_ALIAS, FLAG_LOSE, FLAG_NOPIECE, FLAG_TOPOUT, FLAG_WIN, BatchedTetris
 from .configs import ConfigPool, synthetic_pool
+from .distinct import DISTINCT_MAX
 from .model import ValueNet
 
 # the reference's constants, model/train.py:15-21
@@ -79,6 +88,47 @@ class ReplayMemory:
         return (self.x[idx], self.r[idx], self.done[idx], self.nx[:, idx].permute(1, 0, 2), self.nfl[:, idx].t())
 
 
+class DistinctReplay:
+    """Replay ring for the distinct-placements path: chosen placement (feature word), reward, done, and the next state's
+    placements as a padded [capacity, 34] block of feature words + their count."""
+
+    def __init__(self, capacity: int, device):
+        self.capacity, self.size, self.pos = capacity, 0, 0
+        self.x = torch.zeros(capacity, dtype=torch.int32, device=device)
+        self.r = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self.done = torch.zeros(capacity, dtype=torch.bool, device=device)
+        self.nw = torch.zeros((capacity, DISTINCT_MAX), dtype=torch.int32, device=device)
+        self.ncnt = torch.zeros(capacity, dtype=torch.uint8, device=device)
+
+    def push(self, x, r, done, nw, ncnt):
+        n = min(x.shape[0], self.capacity)
+        first = min(n, self.capacity - self.pos)
+        for lo, hi, at in ((0, first, self.pos), (first, n, 0)):
+            if hi > lo:
+                k = hi - lo
+                self.x[at:at + k], self.r[at:at + k], self.done[at:at + k] = x[lo:hi], r[lo:hi], done[lo:hi]
+                self.nw[at:at + k], self.ncnt[at:at + k] = nw[lo:hi], ncnt[lo:hi]
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch: int, gen, size_t: Optional[torch.Tensor] = None):
+        if size_t is None:
+            idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
+        else:
+            idx = (torch.rand(batch, device=self.x.device) * size_t).long().clamp_(max=self.capacity - 1)
+        return self.x[idx], self.r[idx], self.done[idx], self.nw[idx], self.ncnt[idx]
+
+
+def word_features(words: torch.Tensor) -> torch.Tensor:
+    """feature words (int32, byte 0 = rows cleared | flags << 3) -> float32 [..., 4] = (rows cleared, holes, bumpiness, aggregate height)"""
+    return torch.stack([(words & 7), (words >> 8) & 0xFF, (words >> 16) & 0xFF, (words >> 24) & 0xFF], dim=-1).to(torch.float32)
+
+
+def word_reward(words: torch.Tensor) -> torch.Tensor:
+    """reward_from on feature words"""
+    return reward_from(words & 7, (words >> 3) & 0x1F)
+
+
 @dataclass
 class TrainStats:
     env_steps: int = 0
@@ -112,7 +162,7 @@ def select_slots(values: torch.Tensor, flags: torch.Tensor, eps, gen) -> torch.T
 def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
           config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
           batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True, log_fn=None,
-          cuda_graphs: bool = True) -> tuple:
+          cuda_graphs: bool = True, value_kernel: bool = True) -> tuple:
     """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
     Returns (policy_net, TrainStats).  The action-selection forward pass over the 40 * num_envs afterstate rows runs
     under bf16 autocast (it only ranks slots); the optimiser step stays fp32.
@@ -122,6 +172,9 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
     `optim_steps_per_iter` optimiser steps -- are captured into CUDA graphs and replayed; the env kernel
     (``tpl_step_observe``) and the replay push stay ordinary launches between them."""
     dev = torch.device(device)
+    if value_kernel and dev.type == "cuda":
+        return _train_value_kernel(num_envs, iterations, L, M, dev, seed, config_pool, replay_capacity, optim_steps_per_iter, batch_size,
+                                   log_every, log_fn, cuda_graphs)
     pool = config_pool if config_pool is not None else synthetic_pool(4096, seed=seed, M=M)
     env = BatchedTetris(num_envs, L, M, device=dev, seed=seed, config_pool=pool)
     env.reset()
@@ -223,6 +276,114 @@ def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30
             st.optim_steps += optim_steps_per_iter
         env_events.append((ev0, ev1))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.eps = eps
+        if log_every and (it + 1) % log_every == 0:
+            s = env.reduce_stats()
+            st.loss = float(last_loss.item())
+            if log_fn is not None:
+                log_fn(it + 1, eps, st.loss, s, prev_stats)
+                prev_stats = dict(s)
+                continue
+            print(f"it {it + 1}: eps {eps:.3f} loss {st.loss:.4f} episodes {s['episodes']} wins {s['wins']} "
+                  f"lines/episode {s['lines'] / max(s['episodes'], 1):.2f}")
+    torch.cuda.synchronize(dev)
+    st.total_seconds = time.perf_counter() - t_all
+    st.env_seconds = sum(a.elapsed_time(b) for a, b in env_events) * 1e-3
+    st.loss = float(last_loss.item())
+    s = env.reduce_stats()
+    st.episodes, st.wins = s["episodes"], s["wins"]
+    return policy_net, st
+
+
+def _train_value_kernel(num_envs, iterations, L, M, dev, seed, config_pool, replay_capacity, optim_steps_per_iter, batch_size, log_every,
+                        log_fn, cuda_graphs):
+    """The rollout half on the library's own kernels: per step  pack weights -> tpl_value_rows (tensor cores) -> tpl_select_action ->
+    tpl_step_observe_distinct;  the optimiser half (replay sample, TD target with the target net, Huber loss, AdamW, soft update)
+    in PyTorch, captured into one CUDA graph after three eager iterations."""
+    from .value_kernel import ValueKernel
+    pool = config_pool if config_pool is not None else synthetic_pool(4096, seed=seed, M=M)
+    env = BatchedTetris(num_envs, L, M, device=dev, seed=seed, config_pool=pool)
+    env.reset()
+    torch.manual_seed(seed)
+    policy_net = ValueNet().to(dev)
+    target_net = ValueNet().to(dev)
+    target_net.load_state_dict(policy_net.state_dict())
+    use_graphs = bool(cuda_graphs)
+    optimizer = optim.AdamW(policy_net.parameters(), lr=LR, amsgrad=True, fused=True, capturable=use_graphs)        # model/train.py:27
+    p_params, t_params = list(policy_net.parameters()), list(target_net.parameters())
+    loss_fn = nn.SmoothL1Loss()
+    memory = DistinctReplay(replay_capacity, dev)
+    vk = ValueKernel(policy_net)
+    st = TrainStats()
+    size_t = torch.zeros((), device=dev)
+    last_loss = torch.full((), float("nan"), device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    g_gen = None if use_graphs else gen
+    count_t = torch.as_tensor(_distinct.tables()[0].astype("int64"), device=dev)
+    jj = torch.arange(DISTINCT_MAX, device=dev)
+
+    def optim_block():
+        for _ in range(optim_steps_per_iter):
+            bx, br, bdone, bnw, bcnt = memory.sample(batch_size, g_gen, size_t if use_graphs else None)
+            with torch.no_grad():
+                nv = target_net(word_features(bnw).reshape(-1, 4)).view(batch_size, DISTINCT_MAX)
+                fl = (bnw >> 3) & 0x1F
+                q = (word_reward(bnw) + GAMMA * nv * ((fl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
+                    jj[None, :] >= bcnt[:, None].long(), float("-inf"))
+                best_next = q.max(dim=1).values
+                # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal or nothing to place)
+                target = torch.where(bdone | (bcnt == 0), torch.zeros_like(best_next), best_next)
+            loss = loss_fn(policy_net(word_features(bx)), target)
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_value_(p_params, 100, foreach=True)
+            optimizer.step()
+            with torch.no_grad():                                               # soft update, TAU
+                torch._foreach_mul_(t_params, 1 - TAU)
+                torch._foreach_add_(t_params, p_params, alpha=TAU)
+        last_loss.copy_(loss.detach())
+
+    rows, runs, used = env.afterstates_distinct()
+    vals = torch.zeros(rows.numel(), dtype=torch.float32, device=dev)
+    sel = None
+    g_opt = None
+    t_all = time.perf_counter()
+    env_events, prev_stats = [], {}
+    for it in range(iterations):
+        eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        vk.sync()                                                                 # the optimiser changed the parameters
+        vk.values(rows, used.reshape(1), out=vals)
+        sel = vk.select(rows, runs, vals, GAMMA, eps, seed, it, out=sel)
+        rot, loc, chosen, _ = sel
+        x = chosen.clone()
+        ev0.record()
+        dlines, mflags, state, rows, runs, used = env.step_observe_distinct(rot, loc)
+        ev1.record()
+        reward = reward_from(dlines, mflags)
+        done = state != 0
+        r64 = runs.to(torch.int64) & 0xFFFFFFFF
+        cnt = count_t[r64 >> 29]
+        nw = rows[(r64 & 0x1FFFFFFF)[:, None] + torch.minimum(jj[None, :], (cnt - 1).clamp(min=0)[:, None])]
+        memory.push(x, reward, done, nw, cnt.to(torch.uint8))
+        size_t.fill_(float(memory.size))
+        st.env_steps += num_envs
+        if memory.size >= batch_size:
+            if g_opt is not None:
+                g_opt.replay()
+            elif not use_graphs or it < 3:
+                optim_block()
+            else:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    optim_block()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_opt):
+                    optim_block()
+            st.optim_steps += optim_steps_per_iter
+        env_events.append((ev0, ev1))
         st.eps = eps
         if log_every and (it + 1) % log_every == 0:
             s = env.reduce_stats()

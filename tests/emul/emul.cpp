@@ -157,6 +157,10 @@ int emul_reset_from_pool(void *state, int64_t stride, int n, const void *pool, i
             const uint4 d = st[3 * stride + i];
             const uint32_t s = d.w & 0xFFu, head = (d.w >> 8) & 0xFFu, np = (d.w >> 16) & 0xFFu;
             if (s == S_RUNNING && head < np) continue;
+            if (gen_count > QUEUE_PIECES && s == S_RUNNING) {
+                Env e; load_env(st, stride, i, e);
+                if (refill_queue(e, seed, env_base + (uint64_t)i, ep, gen_count)) { store_env(st, stride, i, e); continue; }
+            }
         }
         if (mode == 2 || (mode == 1 && !idx)) { ep += 1; if (episode) episode[i] = ep; }
         if (tstep) tstep[i] = 0u;
@@ -221,7 +225,8 @@ int emul_step_observe(void *state, int64_t stride, int n, const uint8_t *rot, co
                 if (fl & F_WIN) stats[1] += 1; else if (fl & F_TOPOUT) stats[2] += 1; else stats[3] += 1;
             }
         }
-        if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {
+        if (refill_queue(e, seed, env_base + (uint64_t)i, episode ? episode[i] : 0u, gen_count)) {
+        } else if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {
             uint32_t ep = episode ? episode[i] + 1u : 1u;
             if (episode) episode[i] = ep;
             if (tstep) tstep[i] = 0u;
@@ -238,11 +243,13 @@ int emul_step_observe(void *state, int64_t stride, int n, const uint8_t *rot, co
 }
 
 int emul_gen_pieces(uint8_t *out, int n, int count, uint64_t seed, uint64_t env_base, const uint32_t *episode, uint32_t episode0) {
-    for (int64_t i = 0; i < n; ++i) {
-        uint32_t q[4];
-        gen_queue(seed, env_base + (uint64_t)i, episode ? episode[i] : episode0, count, q);
-        for (int p = 0; p < count; ++p) out[i * count + p] = (uint8_t)queue_piece(q, p);
-    }
+    for (int64_t i = 0; i < n; ++i)
+        for (int base = 0, block = 0; base < count; base += QUEUE_PIECES, ++block) {
+            uint32_t q[4];
+            const int c = count - base < QUEUE_PIECES ? count - base : QUEUE_PIECES;
+            gen_queue(seed, env_base + (uint64_t)i, episode ? episode[i] : episode0, c, q, (uint32_t)block);
+            for (int p = 0; p < c; ++p) out[i * count + base + p] = (uint8_t)queue_piece(q, p);
+        }
     return 0;
 }
 

@@ -129,7 +129,7 @@ class EmulEngine:
         self.L.emul_reset_from_pool(_np_ptr(s.planes), s.stride, s.n, _np_ptr(pool), pool.shape[0], _np_ptr(idx), _np_ptr(mask),
                                     mode, _np_ptr(episode), _np_ptr(tstep), seed, env_base, gen_count)
 
-    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False):
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False, gen_count=0):
         """distinct=True: the afterstates come back as (rows uint32[used], runs uint32[n]) in place of (feats, afl)."""
         n = s.n
         rot = np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8)
@@ -139,7 +139,7 @@ class EmulEngine:
         drows, druns, dcur = (np.zeros(34 * n + 4, np.uint32), np.zeros(n, np.uint32), np.zeros(1, np.uint32)) if distinct else (None, None, None)
         stats = np.zeros(8, np.int64)
         self.L.emul_step_observe(_np_ptr(s.planes), s.stride, n, _np_ptr(rot), _np_ptr(loc), _np_ptr(dl), _np_ptr(fl), _np_ptr(st),
-                                 _np_ptr(stats), _np_ptr(pool), pool.shape[0], _np_ptr(episode), _np_ptr(tstep), seed, env_base, 0,
+                                 _np_ptr(stats), _np_ptr(pool), pool.shape[0], _np_ptr(episode), _np_ptr(tstep), seed, env_base, gen_count,
                                  _np_ptr(feats), _np_ptr(afl), None, L, M, _np_ptr(drows), _np_ptr(druns), _np_ptr(dcur))
         if distinct:
             return dl, fl, st, drows[:int(dcur[0])], druns, stats
@@ -318,7 +318,7 @@ class GpuEngine:
             assert np.array_equal(out.cpu().numpy().transpose(1, 0, 2), dm.expand(r, d)), "tpl_expand_distinct != distinct.expand"
         return r, d
 
-    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False):
+    def step_observe(self, s, rot, loc, pool, episode, seed, env_base, L, M, packed=False, tstep=None, distinct=False, gen_count=0):
         t = self.torch; n = s.n
         rot = self._t(np.mod(np.asarray(rot, np.int64), 4).astype(np.uint8), np.uint8)
         loc = self._t(np.minimum(np.asarray(loc, np.int64), 255).astype(np.uint8), np.uint8)
@@ -331,14 +331,14 @@ class GpuEngine:
             rows, cap, runs, cur, phase = self._distinct_args(n)
             self._chk(self.L.tpl_step_observe_distinct(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
                                                        self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), self._p(d_ts),
-                                                       seed, env_base, 0, self._p(rows), cap, self._p(runs), 0, self._p(cur), phase, L, M,
+                                                       seed, env_base, gen_count, self._p(rows), cap, self._p(runs), 0, self._p(cur), phase, L, M,
                                                        self._stream()), "tpl_step_observe_distinct")
             a, b = self._distinct_result(rows, runs, phase)
         else:
             feats, afl = z((40, n, 4), t.uint8), (None if packed else z((40, n), t.uint8))
             self._chk(self.L.tpl_step_observe(self._p(s.planes), s.stride, n, self._p(rot), self._p(loc), self._p(dl), self._p(fl),
                                               self._p(st), self._p(stats), self._p(pool), pool.shape[0], self._p(d_ep), self._p(d_ts), seed,
-                                              env_base, 0, self._p(feats), self._p(afl), None, L, M, self._stream()), "tpl_step_observe")
+                                              env_base, gen_count, self._p(feats), self._p(afl), None, L, M, self._stream()), "tpl_step_observe")
             a, b = feats.cpu().numpy(), (None if afl is None else afl.cpu().numpy())
         episode[:] = d_ep.cpu().numpy().view(np.uint32)
         if tstep is not None:

@@ -252,6 +252,11 @@ def case_rng(eng):
             srt = np.sort(grp, axis=1)
             assert (srt[:, 1:] != srt[:, :-1]).all()
             assert grp.max() <= 6
+    # sequences longer than the 42-piece queue (block-wise generation == the oracle's bag-by-bag definition)
+    for count in (43, 61, 84, 100, 300):
+        got = eng.gen_pieces(33, count, 21, 5, 2)
+        assert np.array_equal(got, c_oracle.gen_pieces(21, 5, 33, 2, count))
+        assert list(got[7]) == po.gen_pieces(21, 5 + 7, 2, count)
     ep = np.arange(300, dtype=np.uint32) * 3
     got = eng.gen_pieces(300, 31, 9, 77, episode=ep)
     for e in (0, 17, 299):
@@ -391,6 +396,60 @@ def case_fused_step_observe(eng, pool_arrays, n=3000, steps=45, L=10, M=30, seed
             ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
         assert_same(eng, a, ost, f"fused step {t}")
     assert tot[6] == n * steps and (tot[0] > 0 or steps < 30) and tot[7] == tot[0]
+
+
+def case_long_episodes(eng, n=400, L=200, M=60, seed=13, env_base=1 << 21):
+    """Episodes longer than the 42-piece queue (M = 60 -> 61 pieces): the kernels refill the queue from the counter-based
+    sequence when it runs dry (game/tetris.py:95-102: sequences of any length).  Driven by a host-side greedy heuristic on the
+    oracle's afterstate features so that episodes actually last 60 moves; even steps go through the fused step, odd steps
+    through tpl_step + tpl_reset_from_pool(TPL_RESET_DONE), which refills as well."""
+    G = M + 1
+    rng = np.random.default_rng(seed)
+    K = 16
+    prow = np.zeros((K, 20), np.uint16)
+    prow[1:, 19] = rng.integers(1, 1023, K - 1).astype(np.uint16)               # (almost) empty boards: long episodes
+    ppieces, pnp = np.zeros((K, P), np.uint8), np.full(K, 1, np.uint8)
+    pool = eng.make_pool(prow, ppieces, pnp)
+    idx = rng.integers(0, K, n).astype(np.int32)
+    s = eng.empty_states(n)
+    ep = np.zeros(n, np.uint32)
+    eng.reset(s, pool, idx=idx, episode=ep, seed=seed, env_base=env_base, gen_count=G)
+    ost = c_oracle.BatchState(n, P=64)
+    seq = c_oracle.gen_pieces(seed, env_base, n, 0, G)
+    ost.load(prow[idx], seq, np.full(n, G, np.uint8))
+    oep = np.zeros(n, np.uint32)
+    longest = 0
+    for t in range(M + 25):
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M)
+        bad = (ofl & (FLAG_TOPOUT | FLAG_ALIAS | FLAG_NOPIECE)) != 0
+        score = of[:, :, 1].astype(np.int64) * 8 + of[:, :, 3].astype(np.int64) + of[:, :, 2].astype(np.int64) - 20 * of[:, :, 0].astype(np.int64)
+        slot = np.where(bad, 1 << 30, score).argmin(axis=1)
+        rot, loc = slot // 10, slot % 10
+        if t % 2 == 0:
+            dl, fl, st, _, _, _ = eng.step_observe(s, rot, loc, pool, ep, seed, env_base, L, M, packed=True, gen_count=G)
+        else:
+            dl, fl, st = eng.step(s, rot, loc, L, M)
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        assert np.array_equal(dl, odl) and np.array_equal(st, ost.state), f"step {t}"
+        longest = max(longest, int(ost.moves.max()))
+        # episodes that ended start the next one: same board class (explicit idx is not available to the fused step, so the
+        # config is the counter-RNG draw), a fresh 61-piece sequence keyed by the new episode number
+        done = np.where((ost.state != 0) | (ost.head >= ost.npieces))[0]
+        for i in done:
+            oep[i] += 1
+            k = po.config_index(seed, env_base + int(i), int(oep[i]), K)
+            ost.rows[i] = prow[k]; ost.pieces[i] = 0
+            ost.pieces[i, :G] = c_oracle.gen_pieces(seed, env_base + int(i), 1, int(oep[i]), G)[0]
+            ost.npieces[i] = G; ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
+        if t % 2 == 1:
+            eng.reset(s, pool, mode=2, episode=ep, seed=seed, env_base=env_base, gen_count=G)
+        u = eng.unpack(s)
+        assert np.array_equal(ep, oep), f"step {t}: episode numbers"
+        assert np.array_equal(u["rows"], ost.rows) and np.array_equal(u["lines"], ost.lines), f"step {t}: boards / lines"
+        assert np.array_equal(u["moves"], ost.moves) and np.array_equal(u["state"], ost.state), f"step {t}: moves / state"
+        cur = ost.pieces[np.arange(n), np.minimum(ost.head, 63)]
+        assert np.array_equal(u["cur"], np.where(ost.head < ost.npieces, cur, 255).astype(np.uint8)), f"step {t}: current piece"
+    assert longest == M, f"no episode reached the move limit ({longest})"
 
 
 # ---------------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ def test_argument_errors_need_no_gpu(tp):
     L = tp._lib.lib()
     assert L.tpl_step(None, 0, 4, None, None, None, None, None, None, 1, 1, None) == -1
     assert b"null" in L.tpl_last_error()
-    assert L.tpl_gen_pieces(ctypes.c_void_p(8), 4, 99, 0, 0, None, 0, None) == -2
+    assert L.tpl_gen_pieces(ctypes.c_void_p(8), 4, 42 * 256 + 1, 0, 0, None, 0, None) == -2      # sequences of any length up to 42 * 256
     assert L.tpl_afterstates(ctypes.c_void_p(8), 2, 4, ctypes.c_void_p(8), None, None, 1, 1, None) == -2   # stride < n
     assert L.tpl_pack(ctypes.c_void_p(8), 0, 0, 0, ctypes.c_void_p(8), ctypes.c_void_p(8), 1, ctypes.c_void_p(8),
                       None, None, None, None, None) == 0                                                      # n == 0 is a no-op

@@ -61,3 +61,7 @@ def test_fused_step_observe(emul, golden_dir):
 
 def test_edges(emul):
     pc.case_edges(emul)
+
+
+def test_long_episodes_queue_refill(emul):
+    pc.case_long_episodes(emul)

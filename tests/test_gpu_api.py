@@ -294,7 +294,7 @@ def test_error_codes(tp):
     L = tp._lib.lib()
     assert L.tpl_step(None, 0, 4, None, None, None, None, None, None, 1, 1, None) == -1
     assert b"null" in L.tpl_last_error()
-    assert L.tpl_gen_pieces(ctypes.c_void_p(8), 4, 99, 0, 0, None, 0, None) == -2
+    assert L.tpl_gen_pieces(ctypes.c_void_p(8), 4, 42 * 256 + 1, 0, 0, None, 0, None) == -2
     with pytest.raises(tp.TplError):
         tp._lib.check(L.tpl_afterstates(ctypes.c_void_p(8), 0, 4, None, None, None, 1, 1, None), "x")
     h = tp.HostBatchedTetris(4, 3, 3)

@@ -144,3 +144,56 @@ def test_compact_form_64bit_pointer_chain(gpu, golden_dir):
     env = dict(os.environ, TPL_NO_P32="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "chain64-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("log2n", [22, 23])
+def test_big_batches_vs_oracle(gpu, golden_dir, log2n):
+    """2^22 and 2^23 envs (BASELINE configs[4]: 8 M envs over 2 / 4 GPUs = 4 M / 2 M per GPU) against the C ORACLE, not against the
+    stand-alone kernels: fused random rollout (boards, queues, counters, episode numbers, statistics), then two fused steps with
+    external actions (compact 40-slot form, then the distinct-placements form) incl. the auto-reset and every afterstate word."""
+    import torch
+    import tetris_piclim as tp
+    from oracle import c_oracle
+    n, L, M, seed, base = 1 << log2n, 10, 30, 77, 1 << 36
+    prow, ppieces, pnp = _pool(golden_dir)
+    pool = tp.ConfigPool(prow, ppieces, pnp)
+    env = tp.BatchedTetris(n, L, M, seed=seed, config_pool=pool, env_base=base)
+    env.reset()
+    ost = c_oracle.BatchState(n)
+    oep, ots, ostats = c_oracle.rollout(ost, base, seed, L, M, prow, ppieces, pnp, 0, True)
+    env.rollout_random(9)
+    _, _, s1 = c_oracle.rollout(ost, base, seed, L, M, prow, ppieces, pnp, 9, False, oep, ots, nthreads=16)
+    assert np.array_equal(env.stats.cpu().numpy(), s1)
+
+    def same_state(what):
+        f = env.fields()
+        for k, o in (("rows", ost.rows), ("state", ost.state), ("lines", ost.lines), ("moves", ost.moves), ("head", ost.head)):
+            assert np.array_equal(f[k].cpu().numpy(), o), f"{what}: {k}"
+        assert np.array_equal(env.episode.cpu().numpy().view(np.uint32), oep), what
+    same_state("after the fused rollout")
+    rng = np.random.default_rng(log2n)
+    for t, distinct in enumerate((False, True)):
+        rot, loc = rng.integers(0, 4, n).astype(np.uint8), rng.integers(0, 10, n).astype(np.uint8)
+        d_rot, d_loc = torch.from_numpy(rot).cuda(), torch.from_numpy(loc).cuda()
+        if distinct:
+            dl, fl, st, rows, runs, used = env.step_observe_distinct(d_rot, d_loc)
+        else:
+            dl, fl, st, feats, _, _ = env.step_observe(d_rot, d_loc, packed=True)
+        odl, _ = c_oracle.step_batch(ost, rot, loc, L, M)
+        assert np.array_equal(dl.cpu().numpy(), odl) and np.array_equal(st.cpu().numpy(), ost.state)
+        c_oracle.reset_done(ost, base, seed, prow, ppieces, pnp, oep, ots)
+        same_state(f"fused step {t}")
+        of, ofl, _ = c_oracle.afterstates_batch(ost, L, M, nthreads=16)
+        of[:, :, 0] |= ofl << 3
+        del ofl
+        if distinct:
+            got = env.expand_distinct(rows, runs).permute(1, 0, 2).contiguous().cpu().numpy()
+            assert int(used) < 0.62 * 40 * n
+        else:
+            got = feats.permute(1, 0, 2).contiguous().cpu().numpy()
+        assert np.array_equal(got, of), f"afterstates of fused step {t}"
+        del got, of
+
+
+def test_long_episodes_queue_refill(gpu):
+    pc.case_long_episodes(gpu, n=5000)

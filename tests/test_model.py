@@ -39,8 +39,30 @@ def test_select_slots_never_picks_alias():
 
 
 @pytest.mark.gpu
-def test_dqn_loop_runs_on_gpu(gpu):
+@pytest.mark.parametrize("value_kernel", [True, False])
+def test_dqn_loop_runs_on_gpu(gpu, value_kernel):
     t = _mod("train")
-    net, st = t.train(num_envs=4096, iterations=12, optim_steps_per_iter=2)
+    net, st = t.train(num_envs=4096, iterations=12, optim_steps_per_iter=2, value_kernel=value_kernel)
     assert st.env_steps == 4096 * 12 and st.optim_steps == 24
     assert st.loss == st.loss and st.episodes > 0            # finite loss, episodes finished and were reset
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("value_kernel", [True, False])
+def test_dqn_loop_learns(gpu, value_kernel):
+    """The completed loop (model/train.py's constants) improves the behaviour policy: episodes that end late in a short run clear
+    clearly more lines than those that end early -- on both rollout paths (fused tensor-core ranking kernel over the distinct
+    placements / PyTorch forward over the 40-slot grid)."""
+    import tetris_piclim as tp
+    t = _mod("train")
+    pool = tp.synthetic_pool(4096, seed=0, M=30)
+    log = []
+
+    def cb(it, eps, loss, s, prev):
+        d = {k: s[k] - prev.get(k, 0) for k in s}
+        log.append((d["lines"] / max(d["episodes"], 1), d["moves"] / max(d["episodes"], 1)))
+
+    net, st = t.train(num_envs=8192, iterations=900, config_pool=pool, optim_steps_per_iter=8, batch_size=1024, log_every=150, log_fn=cb,
+                      value_kernel=value_kernel)
+    assert len(log) == 6 and st.loss == st.loss
+    assert log[-1][0] > 1.5 * log[0][0] and log[-1][1] > log[0][1], log      # more lines and longer episodes

@@ -129,3 +129,28 @@ def test_oracles_vs_live_reference_sample():
     check_tables(refshim.load())
     moves, topouts, wins = run_chunk((99, 300))
     assert moves > 1500
+
+
+def test_c_reset_done_matches_python_config_draw(golden_dir):
+    """orc_reset_done (the C statement of the fused step's auto-reset) == the per-env Python restatement"""
+    import os
+    from oracle import c_oracle, piclim_oracle as po
+    z = np.load(os.path.join(golden_dir, "carve_pool_L10_M30.npz"))
+    prow, ppieces, pnp = z["rows"], z["pieces"], z["npieces"]
+    n, seed, base = 500, 7, 1 << 34
+    st = c_oracle.BatchState(n)
+    ep, ts, _ = c_oracle.rollout(st, base, seed, 10, 30, prow, ppieces, pnp, 12, True)
+    ref = st.copy(); ep_ref = ep.copy()
+    done = (ref.state != 0) | (ref.head >= ref.npieces)
+    assert done.any() and not done.all()
+    ts[:] = 5
+    cnt = c_oracle.reset_done(st, base, seed, prow, ppieces, pnp, ep, ts)
+    assert cnt == int(done.sum())
+    for i in range(n):
+        if done[i]:
+            k = po.config_index(seed, base + i, int(ep_ref[i]) + 1, len(prow))
+            assert ep[i] == ep_ref[i] + 1 and ts[i] == 0
+            assert np.array_equal(st.rows[i], prow[k]) and st.npieces[i] == pnp[k] and st.head[i] == 0 and st.state[i] == 0
+            assert np.array_equal(st.pieces[i, :pnp[k]], ppieces[k, :pnp[k]]) and st.lines[i] == 0 and st.moves[i] == 0
+        else:
+            assert ep[i] == ep_ref[i] and ts[i] == 5 and np.array_equal(st.rows[i], ref.rows[i])
