@@ -611,11 +611,41 @@ def dqn_leg(tp, torch, dev):
     """BASELINE configs[3]: the DQN afterstate-value loop (model/train.py's constants) driving 65 536 GPU envs, ~30 iterations."""
     from importlib import import_module
     train = import_module(tp.__name__ + ".train")
-    iters = 40
+    iters = 100
+    train.train(num_envs=65536, iterations=6, device=dev, seed=0, log_every=0)          # warm-up: allocator, cuBLAS handles
     net, st = train.train(num_envs=65536, iterations=iters, device=dev, seed=0, log_every=0)
-    return {"iterations": iters, "env_steps_per_s_env_only": st.env_steps_per_s, "env_steps_per_s_end_to_end": st.e2e_steps_per_s,
-            "optim_steps": st.optim_steps, "loss": st.loss,
-            "note": "65 536 envs, value net in PyTorch (4-128-128-128-128-1), includes the 3 eager + CUDA-graph-capture iterations"}
+    out = {"iterations": iters, "env_steps_per_s_env_only": st.env_steps_per_s, "env_steps_per_s_end_to_end": st.e2e_steps_per_s,
+           "ms_per_iteration": st.total_seconds * 1e3 / iters, "optim_steps": st.optim_steps, "loss": st.loss,
+           "note": "65 536 envs; rollout half on the library's kernels (tpl_value_rows on the tensor cores over the distinct placements, "
+                   "tpl_select_action, tpl_step_observe_distinct, tpl_replay_push), optimiser half in PyTorch on a second stream: one "
+                   "optimisation step (batch 128) per env step, the structure of the DQN loop model/train.py's constants come from; the "
+                   "timed run includes its own 3 eager iterations and the CUDA-graph capture of the optimiser block"}
+    net4, st4 = train.train(num_envs=65536, iterations=iters // 2, device=dev, seed=0, log_every=0, optim_steps_per_iter=4)
+    out["with_4_optimiser_steps_per_iteration"] = {"env_steps_per_s_end_to_end": st4.e2e_steps_per_s, "ms_per_iteration": st4.total_seconds * 1e3 / (iters // 2),
+                                                   "note": "round 1's setting; the ~100 tiny PyTorch kernels of each optimiser step (about 0.5 ms "
+                                                           "per step, latency-bound) then set the pace"}
+    net5, st5 = train.train(num_envs=65536, iterations=iters // 2, device=dev, seed=0, log_every=0, value_kernel=False)
+    out["pytorch_forward_40_slots"] = {"env_steps_per_s_end_to_end": st5.e2e_steps_per_s, "ms_per_iteration": st5.total_seconds * 1e3 / (iters // 2),
+                                       "note": "same loop with the ranking forward in PyTorch (rank_bf16 over the 40-slot grid, round 1's path)"}
+    # the ranking forward alone: value net over the distinct placements of 65 536 envs
+    vk_mod = import_module(tp.__name__ + ".value_kernel")
+    env = tp.BatchedTetris(65536, L_LINES, M_MOVES, device=dev, seed=SEED, config_pool=tp.synthetic_pool(4096, seed=SEED, M=M_MOVES))
+    env.reset(); env.rollout_random(6); env.reset(done_only=True)
+    rows, runs, used = env.afterstates_distinct()
+    vk = vk_mod.ValueKernel(net)
+    vals = vk.values(rows, used.reshape(1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20):
+        vk.values(rows, used.reshape(1), out=vals)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    R = int(used)
+    flops = 2.0 * R * (16 * 128 + 3 * 128 * 128 + 128)
+    out["value_rows_kernel"] = {"ms": ms, "rows": R, "rows_per_s": R / (ms * 1e-3), "TFLOPs": flops / (ms * 1e-3) / 1e12,
+                                "note": "tpl_value_rows alone: tcgen05 128x128x16 bf16 MMAs, weights + activations on chip; FLOPs counted as "
+                                        "2 * rows * (16*128 + 3*128*128 + 128)"}
+    return out
 
 
 def main():

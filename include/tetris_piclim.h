@@ -190,7 +190,7 @@ int tpl_rollout_greedy(void *state, int64_t plane_stride, int n, const void *poo
  * -> 128 -> 1, inference only, bf16 operands with fp32 accumulation on the tensor cores (tcgen05), weights and activations
  * on chip.  Training stays in PyTorch; these calls only serve the rollout's action selection.  Device pointers.
  * ------------------------------------------------------------------------------------------------- */
-#define TPL_VALUE_BLOB_BYTES 104480
+#define TPL_VALUE_BLOB_BYTES 119328
 /* fp32 parameters in PyTorch layout (weight [out][in]: w1 [128][4], w2..w4 [128][128], w5 [1][128]; biases [128] / [1]) ->
  * the packed bf16 blob (TPL_VALUE_BLOB_BYTES, 16-byte aligned) tpl_value_rows reads.  scale4_host: HOST float[4], the factors the
  * four u8 features (rows cleared, holes, bumpiness, aggregate height) are multiplied by before the first layer. */
@@ -208,6 +208,18 @@ int tpl_value_rows(const uint32_t *rows, const uint32_t *count, int64_t nrows_ma
 int tpl_select_action(const uint32_t *rows, const uint32_t *runs, const float *values, int n, float gamma, float reward_win,
                       float reward_lose, float eps, uint64_t seed, uint64_t env_base, uint32_t step, uint8_t *rot, uint8_t *loc,
                       uint32_t *chosen, float *chosen_q, void *stream);
+
+/* One transition per env from a distinct-form step into the ring buffers of a replay memory (slot = (pos + i) % capacity), in
+ * the form a TD target consumes without further element-wise work:
+ *   x u32 = the chosen placement's feature word (tpl_select_action) with the flag bits cleared, so that its four bytes ARE the
+ *   features;  reward f32 = rows cleared + reward_win / reward_lose by the move's flags;  live f32 = 0 if the episode ended or
+ *   nothing is left to place, else 1;  next_w u32[capacity][TPL_DISTINCT_MAX] = the new state's placements (flags cleared, zero
+ *   padded);  next_r f32[..][34] = reward of each (-inf past the end of the run; next_r[0] = 0 for an empty run);
+ *   next_g f32[..][34] = gamma where the placement does not end the episode, else 0 -- Q = next_r + next_g * V(next_w).
+ * Device pointers; one launch instead of a few dozen framework ops per rollout step. */
+int tpl_replay_push(const uint32_t *rows, const uint32_t *runs, const int8_t *dlines, const uint8_t *mflags, const int8_t *state,
+                    const uint32_t *chosen, int n, int64_t pos, int64_t capacity, float gamma, float reward_win, float reward_lose,
+                    uint32_t *x, float *reward, float *live, uint32_t *next_w, float *next_r, float *next_g, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * host-buffer API (handle owns device memory; every array is a HOST pointer)

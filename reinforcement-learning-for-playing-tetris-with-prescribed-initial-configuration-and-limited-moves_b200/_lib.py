@@ -28,6 +28,7 @@ DEVICE_API = {
     "expand_distinct": (c_int, [P, P, c_int, P, P]),
     "value_pack": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "value_rows": (c_int, [P, P, c_int64, P, P, P]),
+    "replay_push": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int64, c_float, c_float, c_float, P, P, P, P, P, P, P]),
     "select_action": (c_int, [P, P, P, c_int, c_float, c_float, c_float, c_float, c_uint64, c_uint64, c_uint32, P, P, P, P, P]),
     "gen_pieces": (c_int, [P, c_int, c_int, c_uint64, c_uint64, P, c_uint32, P]),
     "rollout_random": (c_int, [P, c_int64, c_int, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int, c_int, c_int, P]),

@@ -378,6 +378,19 @@ __device__ __forceinline__ void gen_queue(uint64_t seed, uint64_t env, uint32_t 
     q[0] = (uint32_t)lo; q[1] = (uint32_t)(lo >> 32); q[2] = (uint32_t)hi; q[3] = (uint32_t)(hi >> 32);
 }
 
+// Out-of-line copy for the kernels' hot loops: a queue is generated only when an env is reset in generate mode or runs dry
+// mid-episode, and two inlined Philox calls per call site would only bloat the loop bodies the instruction cache has to hold.
+#ifdef TPL_HOST_EMUL
+#define TPL_NOINLINE
+#else
+#define TPL_NOINLINE __noinline__
+#endif
+static __device__ TPL_NOINLINE uint4 gen_queue_cold(uint64_t seed, uint64_t env, uint32_t episode, int count, uint32_t block) {
+    uint32_t q[4];
+    gen_queue(seed, env, episode, count, q, block);
+    return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
 constexpr int QUEUE_PIECES = 42;                 // pieces the 128-bit queue holds
 constexpr int GEN_MAX = QUEUE_PIECES * 256;      // longest generated sequence (the block number is one byte of the record)
 
@@ -390,7 +403,8 @@ __device__ __forceinline__ bool refill_queue(Env &e, uint64_t seed, uint64_t env
     if (done >= gen_total) return false;
     e.qblock += 1u;
     const int count = min(QUEUE_PIECES, gen_total - done);
-    gen_queue(seed, env, episode, count, e.q, e.qblock);
+    const uint4 q = gen_queue_cold(seed, env, episode, count, e.qblock);
+    e.q[0] = q.x; e.q[1] = q.y; e.q[2] = q.z; e.q[3] = q.w;
     e.head = 0; e.npieces = (uint32_t)count;
     return true;
 }

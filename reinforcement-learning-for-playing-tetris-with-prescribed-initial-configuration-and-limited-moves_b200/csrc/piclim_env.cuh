@@ -47,7 +47,8 @@ __device__ __forceinline__ void install_config(Env &e, const uint4 *__restrict__
     e.lines = 0; e.moves = 0; e.state = S_RUNNING; e.head = 0; e.qblock = 0;
     if (gen_count > 0) {                      // (more than 42: the first block now, the rest by refill_queue as the episode goes on)
         const int first = gen_count < QUEUE_PIECES ? gen_count : QUEUE_PIECES;
-        gen_queue(seed, env, episode, first, e.q); e.npieces = (uint32_t)first;
+        const uint4 q = gen_queue_cold(seed, env, episode, first, 0u);
+        e.q[0] = q.x; e.q[1] = q.y; e.q[2] = q.z; e.q[3] = q.w; e.npieces = (uint32_t)first;
     }
 }
 

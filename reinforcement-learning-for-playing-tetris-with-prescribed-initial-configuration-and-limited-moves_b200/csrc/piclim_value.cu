@@ -7,8 +7,10 @@
 // distinct placement of every env -- 23 N rows -- and PyTorch runs that as five library GEMMs that write the [rows, 128]
 // activations to HBM four times.  Here a CTA keeps all weights in shared memory and the activations on chip:
 //   rows (u32 feature words, the distinct-placements form)  ->  bf16 A tile [128 x 16] in shared memory (features * scale, a
-//   constant 1 that carries the first bias)  ->  UMMA 128x128x16  ->  TMEM  ->  registers: ReLU, bf16  ->  shared memory  ->
-//   UMMA 128x128x128 (three times, bias + ReLU in the epilogue)  ->  registers: dot with the last layer  ->  values f32[rows].
+//   constant 1 that carries the first bias)  ->  UMMA 128x128x16  ->  TMEM  ->  registers: ReLU + bf16 in one cvt per two
+//   elements  ->  shared memory  ->  UMMA 128x128x144 (three times; the ninth K-step multiplies a constant-1 column with the
+//   bias row, so the epilogue has no bias add)  ->  UMMA 128x16x144 (the last layer, N padded)  ->  one TMEM load per row  ->
+//   values f32[rows].
 // bf16 operands, fp32 accumulation: the numerics of ValueNet.rank_bf16.  Two 128-row tiles are in flight per CTA (two groups of
 // four warps, each with its own accumulator columns, activation buffer and mbarrier), so one group's epilogue overlaps the
 // other's MMAs.  Operand tiles use the canonical K-major no-swizzle UMMA layout: 8-row x 16-byte core matrices, the two
@@ -27,20 +29,27 @@ int check_launch(const char *what);
 namespace tplv {
 
 constexpr int HID = 128;                         // hidden width (model/model.py:9-13)
+constexpr int KAUG = HID + 16;                   // K of the hidden layers: 128 activations + one K-step whose first column is the constant 1
+                                                 // that carries the bias (the other 15 are zero) -- no bias add in the epilogue
+constexpr int NOUT = 16;                         // the last layer (128 -> 1) as an MMA too: N padded to the smallest UMMA N for M = 128
 constexpr int TILE_ROWS = 128;                   // UMMA M
 constexpr int GROUPS = 2;                        // tiles in flight per CTA
 constexpr int VTHREADS = GROUPS * 128;
 // ---- packed weight blob (device memory, copied to shared memory by every CTA); byte offsets
-constexpr int OFF_W1 = 0;                        // [128 n][16 k] bf16: k < 4 weights, k == 4 bias, rest 0     (4 KB)
-constexpr int OFF_W2 = 4096;                     // [128 n][128 k] bf16 x 3                                    (32 KB each)
-constexpr int OFF_B = OFF_W2 + 3 * 32768;        // f32: b2[128] b3[128] b4[128] w5[128] b5 scale[4] pad[3]
-constexpr int BLOB_BYTES = OFF_B + (4 * 128 + 8) * 4;
+constexpr int OFF_W1 = 0;                        // [128 n][16 k] bf16: k < 4 weights, k == 4 bias, rest 0                       (4 KB)
+constexpr int W_BYTES = HID * KAUG * 2;          // [128 n][144 k] bf16: k < 128 weights, k == 128 bias, rest 0                  (36 KB)
+constexpr int OFF_W2 = 4096;                     // three of them
+constexpr int OFF_W5 = OFF_W2 + 3 * W_BYTES;     // [16 n][144 k] bf16: row 0 = last layer's weights and bias, rows 1..15 zero  (4.5 KB)
+constexpr int OFF_B = OFF_W5 + NOUT * KAUG * 2;  // f32: scale[4], pad[4]
+constexpr int BLOB_BYTES = OFF_B + 32;
 static_assert(BLOB_BYTES % 16 == 0 && BLOB_BYTES == TPL_VALUE_BLOB_BYTES, "blob size is part of the ABI");
 // ---- shared memory
-constexpr int OFF_A0 = BLOB_BYTES;               // per group: input tile [128 x 16] bf16 (4 KB), then activations [128 x 128] bf16 (32 KB)
-constexpr int GROUP_BYTES = 4096 + 32768;
+constexpr int OFF_A0 = BLOB_BYTES;               // per group: input tile [128 x 16] bf16 (4 KB), then activations [128 x 144] bf16 (36 KB)
+constexpr int ACT_BYTES = TILE_ROWS * KAUG * 2;
+constexpr int GROUP_BYTES = 4096 + ACT_BYTES;
 constexpr int OFF_BAR = OFF_A0 + GROUPS * GROUP_BYTES;       // 2 mbarriers + the TMEM base address
 constexpr int SMEM_BYTES = OFF_BAR + 32;
+constexpr int TMEM_COLS = 512;                   // per group 128 accumulator columns + 16 for the last layer, at a 256-column pitch
 
 // canonical K-major, no swizzle: element (row, k) of a [rows x K] bf16 tile
 __host__ __device__ constexpr uint32_t canon_off(uint32_t row, uint32_t k, uint32_t K) {
@@ -60,19 +69,23 @@ __global__ void pack_kernel(const float *w1, const float *b1, const float *w2, c
         const float v = k < 4 ? w1[n * 4 + k] : (k == 4 ? b1[n] : 0.0f);
         W1[canon_off(n, k, 16) / 2] = __float2bfloat16_rn(v);
     }
-    const float *ws[3] = {w2, w3, w4};
+    const float *ws[3] = {w2, w3, w4}, *bs[3] = {b2, b3, b4};
     for (int l = 0; l < 3; ++l) {
-        __nv_bfloat16 *W = reinterpret_cast<__nv_bfloat16 *>(blob + OFF_W2 + l * 32768);
-        for (int e = tid; e < HID * HID; e += nth) {
-            const int n = e >> 7, k = e & 127;
-            W[canon_off(n, k, HID) / 2] = __float2bfloat16_rn(ws[l][n * HID + k]);
+        __nv_bfloat16 *W = reinterpret_cast<__nv_bfloat16 *>(blob + OFF_W2 + l * W_BYTES);
+        for (int e = tid; e < HID * KAUG; e += nth) {
+            const int n = e / KAUG, k = e - n * KAUG;
+            const float v = k < HID ? ws[l][n * HID + k] : (k == HID ? bs[l][n] : 0.0f);
+            W[canon_off(n, k, KAUG) / 2] = __float2bfloat16_rn(v);
         }
     }
-    float *B = reinterpret_cast<float *>(blob + OFF_B);
-    for (int e = tid; e < HID; e += nth) {
-        B[e] = bf16_round(b2[e]); B[HID + e] = bf16_round(b3[e]); B[2 * HID + e] = bf16_round(b4[e]); B[3 * HID + e] = bf16_round(w5[e]);
+    __nv_bfloat16 *W5 = reinterpret_cast<__nv_bfloat16 *>(blob + OFF_W5);
+    for (int e = tid; e < NOUT * KAUG; e += nth) {
+        const int n = e / KAUG, k = e - n * KAUG;
+        const float v = n == 0 ? (k < HID ? w5[k] : (k == HID ? b5[0] : 0.0f)) : 0.0f;
+        W5[canon_off(n, k, KAUG) / 2] = __float2bfloat16_rn(v);
     }
-    if (tid == 0) { B[4 * HID] = bf16_round(b5[0]); B[4 * HID + 1] = s0; B[4 * HID + 2] = s1; B[4 * HID + 3] = s2; B[4 * HID + 4] = s3; }
+    float *B = reinterpret_cast<float *>(blob + OFF_B);
+    if (tid == 0) { B[0] = s0; B[1] = s1; B[2] = s2; B[3] = s3; B[4] = B[5] = B[6] = B[7] = 0.0f; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -86,12 +99,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+constexpr uint32_t idesc_for(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
+constexpr uint32_t IDESC_HID = idesc_for(HID), IDESC_OUT = idesc_for(NOUT);
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar_saddr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_saddr) : "memory");
@@ -116,21 +130,39 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
 
-// 32 consecutive accumulator columns of this thread's TMEM lane (warp-collective)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 32 consecutive accumulator columns of this thread's TMEM lane (warp-collective); issue only -- tmem_ld_wait() completes it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-                 "tcgen05.wait::ld.sync.aligned;\n"          /* same statement: the registers are valid when it ends */
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
+// All tensor-memory loads of this thread have landed.  The empty volatile statements pin every destination register behind the
+// wait: the compiler orders volatile asm statements, so no use of v[] can be scheduled before the data is there.
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[N]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < N; ++j) asm volatile("" : "+r"(v[j]));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&p);
+}
+// max(x, 0) and the bf16 rounding of two accumulators in ONE instruction
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(uint32_t lo_f32, uint32_t hi_f32) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_f32)), "f"(__uint_as_float(lo_f32)));
+    return d;
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;\n" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -152,23 +184,27 @@ value_rows_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict_
         mbar_init(smem_u32(smem + OFF_BAR), 1); mbar_init(smem_u32(smem + OFF_BAR + 8), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) {                               // warp 0 owns the tensor-memory allocation: 2 x 128 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    if (tid < 32) {                               // warp 0 owns the tensor-memory allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    proxy_fence();                                // the weights were written through the generic proxy, the MMAs read them through the async one
+    uint8_t *a0 = smem + OFF_A0 + g * GROUP_BYTES, *act = a0 + 4096;
+    const uint32_t my_a0 = canon_off((uint32_t)tg, 0, 16), my_act = canon_off((uint32_t)tg, 0, KAUG);
+    // the bias K-step of this row of the activation tile, written once: (1, 0, ..., 0)
+    *reinterpret_cast<uint4 *>(act + my_act + (HID / 8) * 128u) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(act + my_act + (HID / 8 + 1) * 128u) = make_uint4(0u, 0u, 0u, 0u);
+    proxy_fence();                                // weights and bias columns were written through the generic proxy, the MMAs read through the async one
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot + (uint32_t)g * HID;               // this group's accumulator: 128 lanes x 128 columns
+    const uint32_t tmem_d = *tmem_slot + (uint32_t)g * 256u;              // this group's accumulators: 128 lanes x (128 + 16) columns
     const uint32_t tmem_mine = tmem_d + ((uint32_t)(wq * 32) << 16);      // the 32 lanes this warp may read
-    uint8_t *a0 = smem + OFF_A0 + g * GROUP_BYTES, *act = a0 + 4096;
     const float *B = reinterpret_cast<const float *>(smem + OFF_B);
-    const float sc0 = B[4 * HID + 1], sc1 = B[4 * HID + 2], sc2 = B[4 * HID + 3], sc3 = B[4 * HID + 4], b5 = B[4 * HID];
+    const float sc0 = B[0], sc1 = B[1], sc2 = B[2], sc3 = B[3];
     const uint32_t nrows = count ? min(*count, nrows_max) : nrows_max;
     const uint32_t ntiles = (nrows + TILE_ROWS - 1) / TILE_ROWS;
     uint32_t parity = 0;
-    const uint32_t my_a0 = canon_off((uint32_t)tg, 0, 16), my_act = canon_off((uint32_t)tg, 0, HID);
+    const uint32_t abase = smem_u32(act);
 
     for (uint32_t tile = blockIdx.x * GROUPS + g; tile < ntiles; tile += gridDim.x * GROUPS) {
         const uint32_t row = tile * TILE_ROWS + (uint32_t)tg;
@@ -183,53 +219,55 @@ value_rows_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict_
         group_sync(g);
         if (tg == 0) {                            // layer 1: one 128 x 128 x 16 instruction
             tc_fence_after();
-            umma_f16(tmem_d, umma_desc(smem_u32(a0), 128, 256), umma_desc(smem_u32(smem + OFF_W1), 128, 256), 0u);
+            umma_f16(tmem_d, umma_desc(smem_u32(a0), 128, 256), umma_desc(smem_u32(smem + OFF_W1), 128, 256), IDESC_HID, 0u);
             umma_commit(bar);
         }
-        float value = b5;
 #pragma unroll 1
         for (int layer = 1; layer <= 4; ++layer) {
             mbar_wait(bar, parity); parity ^= 1u;
             tc_fence_after();
-            const float *bias = layer >= 2 ? B + (layer - 2) * HID : nullptr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < HID; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_mine + (uint32_t)c0, v);
-                float h[32];
+            // epilogue of a hidden layer: accumulator -> ReLU -> bf16 -> the next MMA's A operand (canonical layout: 8 columns =
+            // one 16-byte chunk); the bias came in through the constant-1 column, so there is one instruction per two elements
+            {
+                uint32_t v[HID];                  // the whole row of the accumulator: four loads in flight, ONE wait
 #pragma unroll
-                for (int j = 0; j < 32; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + (bias ? bias[c0 + j] : 0.0f), 0.0f);
-                if (layer < 4) {                  // next layer's A operand: bf16, canonical layout, 8 columns = one 16-byte chunk
+                for (int c0 = 0; c0 < HID; c0 += 32) tmem_ld32_issue(tmem_mine + (uint32_t)c0, v + c0);
+                tmem_ld_wait(v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4 *>(act + my_act + (uint32_t)(c0 / 8 + q) * 128u) =
-                            make_uint4(pack_bf16x2(h[8 * q], h[8 * q + 1]), pack_bf16x2(h[8 * q + 2], h[8 * q + 3]),
-                                       pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
-                } else {                          // last layer (128 -> 1) on the CUDA cores, from the bf16-rounded activations
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) value = fmaf(bf16_round(h[j]), B[3 * HID + c0 + j], value);
-                }
+                for (int q = 0; q < HID / 8; ++q)
+                    *reinterpret_cast<uint4 *>(act + my_act + (uint32_t)q * 128u) =
+                        make_uint4(relu_pack_bf16x2(v[8 * q], v[8 * q + 1]), relu_pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                   relu_pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), relu_pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
             }
             tc_fence_before();                    // this thread's tensor-memory reads are done before anyone overwrites the accumulator
-            if (layer < 4) {
-                proxy_fence();                    // activations visible to the tensor core's shared-memory reads
-                group_sync(g);
-                if (tg == 0) {
-                    tc_fence_after();
-                    const uint32_t wbase = smem_u32(smem + OFF_W2 + (layer - 1) * 32768), abase = smem_u32(act);
+            proxy_fence();                        // activations visible to the tensor core's shared-memory reads
+            group_sync(g);
+            if (tg == 0) {
+                tc_fence_after();
+                if (layer < 4) {                  // hidden layer: 128 x 128 x 144 = nine K-steps (the ninth adds the bias)
+                    const uint32_t wbase = smem_u32(smem + OFF_W2 + (layer - 1) * W_BYTES);
 #pragma unroll
-                    for (uint32_t k = 0; k < HID / 16; ++k)
-                        umma_f16(tmem_d, umma_desc(abase + k * 256u, 128, 2048), umma_desc(wbase + k * 256u, 128, 2048), k);
-                    umma_commit(bar);
+                    for (uint32_t k = 0; k < KAUG / 16; ++k)
+                        umma_f16(tmem_d, umma_desc(abase + k * 256u, 128, KAUG * 16), umma_desc(wbase + k * 256u, 128, KAUG * 16), IDESC_HID, k);
+                } else {                          // last layer: 128 x 16 x 144 into its own accumulator columns
+                    const uint32_t wbase = smem_u32(smem + OFF_W5);
+#pragma unroll
+                    for (uint32_t k = 0; k < KAUG / 16; ++k)
+                        umma_f16(tmem_d + HID, umma_desc(abase + k * 256u, 128, KAUG * 16), umma_desc(wbase + k * 256u, 128, KAUG * 16), IDESC_OUT, k);
                 }
+                umma_commit(bar);
             }
         }
+        mbar_wait(bar, parity); parity ^= 1u;
+        tc_fence_after();
+        const float value = __uint_as_float(tmem_ld1(tmem_mine + HID));          // column 0 of the last layer's accumulator
         if (row < nrows) values[row] = value;
-        group_sync(g);                            // every lane has read the accumulator before the next tile's first MMA overwrites it
+        tc_fence_before();
+        group_sync(g);                            // every lane has read its value before the next tile's MMAs run
     }
     tc_fence_before();
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*tmem_slot), "r"(256) : "memory");
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*tmem_slot), "r"(TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -272,6 +310,48 @@ select_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ ru
     rot[i] = (uint8_t)r_out; loc[i] = (uint8_t)c_out;
     if (chosen) chosen[i] = w_out;
     if (chosen_q) chosen_q[i] = q_out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// replay push: one transition per env straight from the step's outputs into the ring buffers of a DQN replay memory, in the
+// form the TD target consumes without further element-wise work:
+//   x        chosen placement's feature word, flags cleared (bytes = rows cleared, holes, bumpiness, aggregate height)
+//   reward   rows cleared + r_win / r_lose by the move's flags;   live = 0 if the episode ended (or nothing is left to place), else 1
+//   next_w   the new state's distinct placements, flags cleared, zero padded to DISTINCT_MAX
+//   next_r   reward of each of them (-inf past the run's end, so a max over the row ignores the padding)
+//   next_g   gamma where the placement does not end the episode, else 0:  Q(placement) = next_r + next_g * V(placement)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+replay_push_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ runs, const int8_t *__restrict__ dlines,
+                   const uint8_t *__restrict__ mflags, const int8_t *__restrict__ state, const uint32_t *__restrict__ chosen, int n,
+                   int64_t pos, int64_t capacity, float gamma, float r_win, float r_lose, uint32_t *x, float *reward, float *live,
+                   uint32_t *next_w, float *next_r, float *next_g) {
+    __shared__ uint4 s_tab[tpl::TAB_COMPACT4];
+    for (int t = threadIdx.x; t < tpl::TAB_COMPACT4; t += blockDim.x) s_tab[t] = reinterpret_cast<const uint4 *>(&tpl::c_orient)[t];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t slot = (pos + i) % capacity;
+    const uint32_t fl = mflags[i];
+    x[slot] = chosen[i] & ~0xF8u;
+    reward[slot] = (float)dlines[i] + ((fl & tpl::F_WIN) ? r_win : 0.0f) + ((fl & (tpl::F_LOSE | tpl::F_TOPOUT)) ? r_lose : 0.0f);
+    const uint32_t d = runs[i], piece = d >> 29;
+    const uint32_t cnt = piece < 7u ? tpl::orient_run_len(s_tab[piece * 8 + 1]) : 0u;
+    live[slot] = (state[i] != 0 || cnt == 0u) ? 0.0f : 1.0f;
+    const uint32_t *run = rows + (d & 0x1FFFFFFFu);
+    uint32_t *dw = next_w + slot * tpl::DISTINCT_MAX;
+    float *dr = next_r + slot * tpl::DISTINCT_MAX, *dg = next_g + slot * tpl::DISTINCT_MAX;
+    for (uint32_t j = 0; j < (uint32_t)tpl::DISTINCT_MAX; ++j) {
+        uint32_t w = 0u; float r = (j == 0u && cnt == 0u) ? 0.0f : -INFINITY, g = 0.0f;
+        if (j < cnt) {
+            w = run[j];
+            const uint32_t f = (w & 0xFFu) >> 3;
+            r = (float)(w & 7u) + ((f & tpl::F_WIN) ? r_win : 0.0f) + ((f & (tpl::F_LOSE | tpl::F_TOPOUT)) ? r_lose : 0.0f);
+            g = (f & (tpl::F_WIN | tpl::F_LOSE | tpl::F_TOPOUT)) ? 0.0f : gamma;
+            w &= ~0xF8u;
+        }
+        dw[j] = w; dr[j] = r; dg[j] = g;
+    }
 }
 
 }  // namespace tplv
@@ -318,6 +398,19 @@ int tpl_select_action(const uint32_t *rows, const uint32_t *runs, const float *v
     select_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rows, runs, values, n, gamma, reward_win, reward_lose, eps, seed,
                                                                                  env_base, step, rot, loc, chosen, chosen_q);
     return tpl::check_launch("tpl_select_action");
+}
+
+int tpl_replay_push(const uint32_t *rows, const uint32_t *runs, const int8_t *dlines, const uint8_t *mflags, const int8_t *state,
+                    const uint32_t *chosen, int n, int64_t pos, int64_t capacity, float gamma, float reward_win, float reward_lose,
+                    uint32_t *x, float *reward, float *live, uint32_t *next_w, float *next_r, float *next_g, void *stream) {
+    if (!rows || !runs || !dlines || !mflags || !state || !chosen || !x || !reward || !live || !next_w || !next_r || !next_g)
+        return tpl::fail(TPL_EINVAL, "tpl_replay_push: null argument");
+    if (n < 0 || capacity <= 0 || pos < 0 || n > capacity) return tpl::fail(TPL_ERANGE, "tpl_replay_push: need 0 <= n <= capacity, pos >= 0");
+    if (n == 0) return 0;
+    replay_push_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rows, runs, dlines, mflags, state, chosen, n, pos, capacity,
+                                                                                      gamma, reward_win, reward_lose, x, reward, live, next_w,
+                                                                                      next_r, next_g);
+    return tpl::check_launch("tpl_replay_push");
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ Two rollout paths share the optimiser half:
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import time
 from dataclasses import dataclass
@@ -89,25 +90,26 @@ class ReplayMemory:
 
 
 class DistinctReplay:
-    """Replay ring for the distinct-placements path: chosen placement (feature word), reward, done, and the next state's
-    placements as a padded [capacity, 34] block of feature words + their count."""
+    """Replay ring for the distinct-placements path, filled with ONE kernel per rollout step (``tpl_replay_push``) straight from
+    the outputs of ``tpl_step_observe_distinct`` / ``tpl_select_action``, in the form the TD target consumes as is:
+    ``x`` chosen placement (feature word, flags cleared: its four bytes are the features), ``r`` reward, ``live`` 0 where the
+    episode ended, and for the next state's placements ``nw`` [capacity, 34] feature words, ``nr`` their rewards (-inf past the
+    end of the run) and ``ng`` = GAMMA where a placement does not end the episode (else 0): Q = nr + ng * V(nw)."""
 
     def __init__(self, capacity: int, device):
         self.capacity, self.size, self.pos = capacity, 0, 0
         self.x = torch.zeros(capacity, dtype=torch.int32, device=device)
         self.r = torch.zeros(capacity, dtype=torch.float32, device=device)
-        self.done = torch.zeros(capacity, dtype=torch.bool, device=device)
+        self.live = torch.zeros(capacity, dtype=torch.float32, device=device)
         self.nw = torch.zeros((capacity, DISTINCT_MAX), dtype=torch.int32, device=device)
-        self.ncnt = torch.zeros(capacity, dtype=torch.uint8, device=device)
+        self.nr = torch.zeros((capacity, DISTINCT_MAX), dtype=torch.float32, device=device)
+        self.ng = torch.zeros((capacity, DISTINCT_MAX), dtype=torch.float32, device=device)
 
-    def push(self, x, r, done, nw, ncnt):
-        n = min(x.shape[0], self.capacity)
-        first = min(n, self.capacity - self.pos)
-        for lo, hi, at in ((0, first, self.pos), (first, n, 0)):
-            if hi > lo:
-                k = hi - lo
-                self.x[at:at + k], self.r[at:at + k], self.done[at:at + k] = x[lo:hi], r[lo:hi], done[lo:hi]
-                self.nw[at:at + k], self.ncnt[at:at + k] = nw[lo:hi], ncnt[lo:hi]
+    def push_step(self, env, rows, runs, dlines, mflags, state, chosen) -> None:
+        n = min(int(runs.numel()), self.capacity)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+        env._call(env._L.tpl_replay_push, "tpl_replay_push", p(rows), p(runs), p(dlines), p(mflags), p(state), p(chosen), n, self.pos,
+                  self.capacity, GAMMA, 10.0, -10.0, p(self.x), p(self.r), p(self.live), p(self.nw), p(self.nr), p(self.ng), env._stream())
         self.pos = (self.pos + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
@@ -116,17 +118,13 @@ class DistinctReplay:
             idx = torch.randint(0, self.size, (batch,), device=self.x.device, generator=gen)
         else:
             idx = (torch.rand(batch, device=self.x.device) * size_t).long().clamp_(max=self.capacity - 1)
-        return self.x[idx], self.r[idx], self.done[idx], self.nw[idx], self.ncnt[idx]
+        return self.x[idx], self.live[idx], self.nw[idx], self.nr[idx], self.ng[idx]
 
 
-def word_features(words: torch.Tensor) -> torch.Tensor:
-    """feature words (int32, byte 0 = rows cleared | flags << 3) -> float32 [..., 4] = (rows cleared, holes, bumpiness, aggregate height)"""
-    return torch.stack([(words & 7), (words >> 8) & 0xFF, (words >> 16) & 0xFF, (words >> 24) & 0xFF], dim=-1).to(torch.float32)
-
-
-def word_reward(words: torch.Tensor) -> torch.Tensor:
-    """reward_from on feature words"""
-    return reward_from(words & 7, (words >> 3) & 0x1F)
+def clean_word_features(words: torch.Tensor) -> torch.Tensor:
+    """feature words with the flag bits cleared (int32) -> uint8 [..., 4] = (rows cleared, holes, bumpiness, aggregate height):
+    a reinterpretation, no arithmetic"""
+    return words.contiguous().view(torch.uint8).view(*words.shape, 4)
 
 
 @dataclass
@@ -160,10 +158,11 @@ def select_slots(values: torch.Tensor, flags: torch.Tensor, eps, gen) -> torch.T
 
 
 def train(num_envs: int = 65536, iterations: int = 200, L: int = 10, M: int = 30, device="cuda", seed: int = 0,
-          config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 4,
+          config_pool: Optional[ConfigPool] = None, replay_capacity: int = 1 << 20, optim_steps_per_iter: int = 1,
           batch_size: int = BATCH_SIZE, log_every: int = 0, bf16_inference: bool = True, log_fn=None,
           cuda_graphs: bool = True, value_kernel: bool = True) -> tuple:
-    """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each.
+    """Run `iterations` env steps of all envs with `optim_steps_per_iter` optimiser steps each (default 1: one optimisation
+    step per environment step, the structure of the DQN loop the reference's constants -- ``model/train.py:15-21`` -- come from).
     Returns (policy_net, TrainStats).  The action-selection forward pass over the 40 * num_envs afterstate rows runs
     under bf16 autocast (it only ranks slots); the optimiser step stays fp32.
 
@@ -319,21 +318,16 @@ def _train_value_kernel(num_envs, iterations, L, M, dev, seed, config_pool, repl
     last_loss = torch.full((), float("nan"), device=dev)
     gen = torch.Generator(device=dev); gen.manual_seed(seed)
     g_gen = None if use_graphs else gen
-    count_t = torch.as_tensor(_distinct.tables()[0].astype("int64"), device=dev)
-    jj = torch.arange(DISTINCT_MAX, device=dev)
 
     def optim_block():
         for _ in range(optim_steps_per_iter):
-            bx, br, bdone, bnw, bcnt = memory.sample(batch_size, g_gen, size_t if use_graphs else None)
+            bx, blive, bnw, bnr, bng = memory.sample(batch_size, g_gen, size_t if use_graphs else None)
             with torch.no_grad():
-                nv = target_net(word_features(bnw).reshape(-1, 4)).view(batch_size, DISTINCT_MAX)
-                fl = (bnw >> 3) & 0x1F
-                q = (word_reward(bnw) + GAMMA * nv * ((fl & (FLAG_WIN | FLAG_LOSE | FLAG_TOPOUT)) == 0)).masked_fill(
-                    jj[None, :] >= bcnt[:, None].long(), float("-inf"))
-                best_next = q.max(dim=1).values
-                # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal or nothing to place)
-                target = torch.where(bdone | (bcnt == 0), torch.zeros_like(best_next), best_next)
-            loss = loss_fn(policy_net(word_features(bx)), target)
+                nv = target_net(clean_word_features(bnw).reshape(-1, 4)).view(batch_size, DISTINCT_MAX)
+                # V(afterstate) = value of the best continuation from the state it leads to (0 if terminal or nothing to place):
+                # Q(placement) = reward + GAMMA * V unless the placement ends the episode; padding carries -inf
+                target = torch.addcmul(bnr, bng, nv).max(dim=1).values * blive
+            loss = loss_fn(policy_net(clean_word_features(bx)), target)
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
             torch.nn.utils.clip_grad_value_(p_params, 100, foreach=True)
@@ -347,45 +341,49 @@ def _train_value_kernel(num_envs, iterations, L, M, dev, seed, config_pool, repl
     vals = torch.zeros(rows.numel(), dtype=torch.float32, device=dev)
     sel = None
     g_opt = None
+    # The optimiser half runs on its own stream, overlapped with the next rollout step: while the tensor-core kernel ranks the
+    # placements of step k + 1, the (many, tiny) PyTorch kernels of optimiser block k fill the gaps.  Step k + 1 therefore acts
+    # with the parameters block k - 1 produced -- the usual one-step policy lag of an actor / learner split.  Ordering: before
+    # the transitions of step k are pushed, block k - 1 must be complete (it samples the memory); then the weights it produced
+    # are packed for the kernel (vk.sync); then block k starts (it waits for the push and the pack).
+    main = torch.cuda.current_stream(dev)
+    opt_stream = torch.cuda.Stream(device=dev)
+    opt_done = torch.cuda.Event()
+    opt_done.record(main)
     t_all = time.perf_counter()
     env_events, prev_stats = [], {}
     for it in range(iterations):
         eps = EPS_END + (EPS_START - EPS_END) * math.exp(-1.0 * it / EPS_DECAY)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        vk.sync()                                                                 # the optimiser changed the parameters
-        vk.values(rows, used.reshape(1), out=vals)
+        vk.values(rows, used.reshape(1), out=vals)                                # (weights packed at the end of the previous iteration)
         sel = vk.select(rows, runs, vals, GAMMA, eps, seed, it, out=sel)
         rot, loc, chosen, _ = sel
-        x = chosen.clone()
         ev0.record()
         dlines, mflags, state, rows, runs, used = env.step_observe_distinct(rot, loc)
         ev1.record()
-        reward = reward_from(dlines, mflags)
-        done = state != 0
-        r64 = runs.to(torch.int64) & 0xFFFFFFFF
-        cnt = count_t[r64 >> 29]
-        nw = rows[(r64 & 0x1FFFFFFF)[:, None] + torch.minimum(jj[None, :], (cnt - 1).clamp(min=0)[:, None])]
-        memory.push(x, reward, done, nw, cnt.to(torch.uint8))
-        size_t.fill_(float(memory.size))
+        main.wait_event(opt_done)                                                 # block it - 1 is complete: it no longer samples the memory ...
+        memory.push_step(env, rows, runs, dlines, mflags, state, chosen)
+        vk.sync()                                                                 # ... and its parameters are the ones the next step ranks with
         st.env_steps += num_envs
         if memory.size >= batch_size:
-            if g_opt is not None:
-                g_opt.replay()
-            elif not use_graphs or it < 3:
-                optim_block()
-            else:
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
+            opt_stream.wait_stream(main)                                          # the pack has read the weights; the push is in memory
+            with torch.cuda.stream(opt_stream):
+                size_t.fill_(float(memory.size))
+                if g_opt is not None:
+                    g_opt.replay()
+                elif not use_graphs or it < 3:
                     optim_block()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                g_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_opt):
-                    optim_block()
+                else:
+                    optim_block()                                                 # once more outside capture (what capture wants), then captured
+                    g_opt = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_opt, stream=opt_stream):
+                        optim_block()
+                opt_done.record(opt_stream)
             st.optim_steps += optim_steps_per_iter
         env_events.append((ev0, ev1))
         st.eps = eps
         if log_every and (it + 1) % log_every == 0:
+            torch.cuda.synchronize(dev)
             s = env.reduce_stats()
             st.loss = float(last_loss.item())
             if log_fn is not None:

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .model import ValueNet
 
-BLOB_BYTES = 104480
+BLOB_BYTES = 119328          # TPL_VALUE_BLOB_BYTES
 
 
 def _ptr(t):
