@@ -95,9 +95,10 @@ int tpl_env_create(tpl_env **out, int n, int L, int M, int device, uint64_t seed
     e->n = n; e->L = L; e->M = M; e->device = device; e->seed = seed; e->env_base = env_base;
     e->stride = ((int64_t)n + 31) / 32 * 32;
     // chunks of the pipelined step: multiples of 32 envs (a chunk starts on a tile boundary of the state planes), at least
-    // 128 Ki envs each so that a chunk still fills the GPU, at most 4 by default: every chunk costs five small copies, and
-    // the copy engine spends microseconds on each (8 chunks: 2.55 ms per 2^20-env step, 4 chunks: see profiles/)
-    e->nchunks = n / 131072; if (e->nchunks < 1) e->nchunks = 1; if (e->nchunks > 4) e->nchunks = 4;
+    // 256 Ki envs each, two by default -- measured at 2^20 envs (profiles/r02_e2e_chunks.txt): 1 chunk 2.054 ms, 2: 2.047,
+    // 4: 2.104, 8: 2.204 per distinct-form step; the transfer is 1.83 ms of it at the link's rate, so there is little
+    // to overlap and every extra chunk costs five small copies (TPL_ENV_CHUNKS overrides, up to 8)
+    e->nchunks = n / 262144; if (e->nchunks < 1) e->nchunks = 1; if (e->nchunks > 2) e->nchunks = 2;
     if (const char *v = getenv("TPL_ENV_CHUNKS")) { int c = atoi(v); if (c >= 1 && c <= TPL_MAX_CHUNKS) e->nchunks = c; }
     e->chunk_envs = (int)((((int64_t)n + e->nchunks - 1) / e->nchunks + 31) / 32 * 32);
     e->nchunks = (n + e->chunk_envs - 1) / e->chunk_envs;

@@ -188,17 +188,17 @@ def _oracle_autoreset(ost, oep, seed, env_base, pool):
         ost.head[i] = 0; ost.lines[i] = 0; ost.moves[i] = 0; ost.state[i] = 0
 
 
-@pytest.mark.parametrize("n,chunks", [(3000, None), (300_000, None), (70_001, "3")])
+@pytest.mark.parametrize("n,chunks", [(3000, None), (600_000, None), (70_001, "3")])
 def test_host_api_pipelined_and_distinct(tp, carve_pool, n, chunks, monkeypatch):
     """tpl_env_step_observe (40-slot forms) and tpl_env_step_observe_distinct through HOST buffers, with the batch cut into
-    chunks (300 000 envs -> 2 chunks; 70 001 envs forced into 3 ragged chunks): every chunk's results land at the right
+    chunks (600 000 envs -> 2 chunks; 70 001 envs forced into 3 ragged chunks): every chunk's results land at the right
     place of the caller's arrays, and the distinct form expands to the oracle's grid."""
     from tests import parity_cases as pc
     if chunks:
         monkeypatch.setenv("TPL_ENV_CHUNKS", chunks)
     L, M, seed, base = 10, 30, 41, 1 << 35
     envs = [tp.HostBatchedTetris(n, L, M, seed=seed, env_base=base, config_pool=carve_pool) for _ in range(2)]
-    assert envs[0].chunks() == (int(chunks) if chunks else min(4, max(1, n // 131072)))
+    assert envs[0].chunks() == (int(chunks) if chunks else min(2, max(1, n // 262144)))
     for e in envs:
         e.reset()
     ost = c_oracle.BatchState(n)
