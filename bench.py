@@ -56,10 +56,9 @@ def csrc_hash() -> str:
     """sha256 over the kernel sources: ncu-derived numbers are only quoted while they describe THIS build."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, PKG, "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in ("piclim_core.cuh", "piclim_env.cuh", "piclim_kernels.cu", "piclim_value.cu"):       # device code only
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 

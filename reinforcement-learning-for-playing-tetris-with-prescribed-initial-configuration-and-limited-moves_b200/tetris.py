@@ -14,8 +14,9 @@ board, pieces and ``solution`` for that seed and leaves ``random`` where the ref
 ``carve``, ``calculate_drop(_deltas)`` and ``RandomPieceGenerator`` are provided with the reference's signatures, so the
 reference's own test file (``game/main.py``) runs against this module.  ``config_pool=`` switches to drawing from a
 pool with the counter RNG instead.  Differences, all outside the hot path: ``warm_reset=True``
-starts no worker processes (configs are generated on demand, in microseconds-to-milliseconds); the forward generator
-(``game/tetris_algo_main``) is not included; ``render=True`` is not supported (pygame UI).
+starts no worker processes (configs are generated on demand, in microseconds-to-milliseconds); the reference's other
+producer, the forward generator + solver (``game/tetris_algo_main``), is available as ``configs.forward_pool`` /
+``forward_games``; ``render=True`` is not supported (pygame UI).
 Like the reference, ``reset()`` does NOT zero ``lines_cleared``/``moves_used``/``state`` (``:438-443``; only
 the constructor does, ``:149-151``); pass ``fresh=True`` to get an RL-style reset.
 """

@@ -56,7 +56,8 @@ def reward_from(dlines: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
 
 class ReplayMemory:
     """Ring buffer on the device: chosen afterstate (4 x u8), reward, done, and the next state's 40 afterstates
-    (features + flags, u8) for the max in the TD target.  The 40-slot blocks are kept slot-major ([40, capacity, ...]),
+    (features + flags, u8) for the max in the TD target.  (``r``, the reward of the stored move itself, is kept for
+    inspection only: the afterstate value V(x) bootstraps from the NEXT state's placements, whose rewards come from ``nx``.)  The 40-slot blocks are kept slot-major ([40, capacity, ...]),
     the layout the env kernel writes, so a push is 40 contiguous row copies and no transposition."""
 
     def __init__(self, capacity: int, device):
@@ -92,8 +93,8 @@ class ReplayMemory:
 class DistinctReplay:
     """Replay ring for the distinct-placements path, filled with ONE kernel per rollout step (``tpl_replay_push``) straight from
     the outputs of ``tpl_step_observe_distinct`` / ``tpl_select_action``, in the form the TD target consumes as is:
-    ``x`` chosen placement (feature word, flags cleared: its four bytes are the features), ``r`` reward, ``live`` 0 where the
-    episode ended, and for the next state's placements ``nw`` [capacity, 34] feature words, ``nr`` their rewards (-inf past the
+    ``x`` chosen placement (feature word, flags cleared: its four bytes are the features), ``r`` reward of the stored move (kept
+    for inspection; the TD target does not need it), ``live`` 0 where the episode ended, and for the next state's placements ``nw`` [capacity, 34] feature words, ``nr`` their rewards (-inf past the
     end of the run) and ``ng`` = GAMMA where a placement does not end the episode (else 0): Q = nr + ng * V(nw)."""
 
     def __init__(self, capacity: int, device):
