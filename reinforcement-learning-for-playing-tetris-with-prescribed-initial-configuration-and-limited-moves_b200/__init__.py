@@ -17,4 +17,7 @@ def __getattr__(name):          # torch is only imported when the device-tensor 
     if name in ("ValueNet", "Model"):
         from . import model
         return getattr(model, name)
+    if name == "ValueKernel":
+        from .value_kernel import ValueKernel
+        return ValueKernel
     raise AttributeError(name)
