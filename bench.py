@@ -393,34 +393,35 @@ def run_b200(args):
     henv = tp.HostBatchedTetris(n, L_LINES, M_MOVES, device=local, seed=SEED, env_base=rank * n, config_pool=pool)
     henv.reset()
     cap = henv.distinct_capacity()
-    pin = {k: tp.PinnedArray(s, d) for k, (s, d) in dict(rot=((n,), np.uint8), loc=((n,), np.uint8), dl=((n,), np.int8),
-           fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8), rows=((cap,), np.uint32),
-           runs=((n,), np.uint32)).items()}
-    hrot, hloc = rot.cpu().numpy(), loc.cpu().numpy()
     e2e_steps = max(3, min(K, 10))
+    # every step's actions wait in pinned host memory (one row per step, as a host-side policy would leave them); the results
+    # land in pinned host buffers
+    pin = {k: tp.PinnedArray(s, d) for k, (s, d) in dict(rot=((e2e_steps + 2, n), np.uint8), loc=((e2e_steps + 2, n), np.uint8),
+           dl=((n,), np.int8), fl=((n,), np.uint8), st=((n,), np.int8), feats=((40, n, 4), np.uint8), rows=((cap,), np.uint32),
+           runs=((n,), np.uint32)).items()}
+    idx = [i % total for i in range(e2e_steps + 2)]
+    pin["rot"].array[:] = rot[idx].cpu().numpy(); pin["loc"].array[:] = loc[idx].cpu().numpy()
+    out3 = [pin[k].array for k in ("dl", "fl", "st")]
 
     def e2e_leg(call):
         for i in range(2):
-            pin["rot"].array[:] = hrot[i]; pin["loc"].array[:] = hloc[i]
-            call()
+            call(pin["rot"].array[i], pin["loc"].array[i])
         if dist: dist.barrier()
         t0 = time.perf_counter()
         extra = 0
         for i in range(e2e_steps):
-            pin["rot"].array[:] = hrot[(2 + i) % total]; pin["loc"].array[:] = hloc[(2 + i) % total]
-            extra += call() or 0
+            extra += call(pin["rot"].array[2 + i], pin["loc"].array[2 + i]) or 0
         s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if dist: dist.all_reduce(s, op=dist.ReduceOp.MAX)
         return float(s.item()), extra
 
-    base5 = [pin[k].array for k in ("rot", "loc", "dl", "fl", "st")]
     # 40-slot compact form: every slot of the grid crosses PCIe (163 B per env-step)
-    e2e_s, _ = e2e_leg(lambda: henv.step_observe(*base5, pin["feats"].array, None))
+    e2e_s, _ = e2e_leg(lambda r, c: henv.step_observe(r, c, *out3, pin["feats"].array, None))
     # distinct-placements form: only the placements that differ (+ a 4-byte run descriptor per env)
-    e2e_d_s, d_words = e2e_leg(lambda: henv.step_observe_distinct(*base5, pin["rows"].array, pin["runs"].array))
+    e2e_d_s, d_words = e2e_leg(lambda r, c: henv.step_observe_distinct(r, c, *out3, pin["rows"].array, pin["runs"].array))
     # the same call with the features left in HBM (a policy on the GPU reads them there, as train.py does): H2D actions,
     # kernel, D2H of (rows cleared, flags, state) only
-    e2e_dev_s, _ = e2e_leg(lambda: henv.step_observe(*base5, None, None))
+    e2e_dev_s, _ = e2e_leg(lambda r, c: henv.step_observe(r, c, *out3, None, None))
     chunks = henv.chunks()
     henv.close()
     # PCIe reference for the e2e figures: D2H of a pinned buffer the size of one step's 40-slot output, all ranks at once
@@ -612,44 +613,16 @@ def extra_single_gpu(tp, torch, dev, pool, args):
 
 
 def dqn_leg(tp, torch, dev):
-    """BASELINE configs[3]: the DQN afterstate-value loop (model/train.py's constants) driving 65 536 GPU envs, ~30 iterations."""
-    from importlib import import_module
-    train = import_module(tp.__name__ + ".train")
-    iters = 100
-    train.train(num_envs=65536, iterations=6, device=dev, seed=0, log_every=0)          # warm-up: allocator, cuBLAS handles
-    net, st = train.train(num_envs=65536, iterations=iters, device=dev, seed=0, log_every=0)
-    out = {"iterations": iters, "env_steps_per_s_env_only": st.env_steps_per_s, "env_steps_per_s_end_to_end": st.e2e_steps_per_s,
-           "ms_per_iteration": st.total_seconds * 1e3 / iters, "optim_steps": st.optim_steps, "loss": st.loss,
-           "note": "65 536 envs; rollout half on the library's kernels (tpl_value_rows on the tensor cores over the distinct placements, "
-                   "tpl_select_action, tpl_step_observe_distinct, tpl_replay_push), optimiser half in PyTorch on a second stream: one "
-                   "optimisation step (batch 128) per env step, the structure of the DQN loop model/train.py's constants come from; the "
-                   "timed run includes its own 3 eager iterations and the CUDA-graph capture of the optimiser block"}
-    net4, st4 = train.train(num_envs=65536, iterations=iters // 2, device=dev, seed=0, log_every=0, optim_steps_per_iter=4)
-    out["with_4_optimiser_steps_per_iteration"] = {"env_steps_per_s_end_to_end": st4.e2e_steps_per_s, "ms_per_iteration": st4.total_seconds * 1e3 / (iters // 2),
-                                                   "note": "round 1's setting; the ~100 tiny PyTorch kernels of each optimiser step (about 0.5 ms "
-                                                           "per step, latency-bound) then set the pace"}
-    net5, st5 = train.train(num_envs=65536, iterations=iters // 2, device=dev, seed=0, log_every=0, value_kernel=False)
-    out["pytorch_forward_40_slots"] = {"env_steps_per_s_end_to_end": st5.e2e_steps_per_s, "ms_per_iteration": st5.total_seconds * 1e3 / (iters // 2),
-                                       "note": "same loop with the ranking forward in PyTorch (rank_bf16 over the 40-slot grid, round 1's path)"}
-    # the ranking forward alone: value net over the distinct placements of 65 536 envs
-    vk_mod = import_module(tp.__name__ + ".value_kernel")
-    env = tp.BatchedTetris(65536, L_LINES, M_MOVES, device=dev, seed=SEED, config_pool=tp.synthetic_pool(4096, seed=SEED, M=M_MOVES))
-    env.reset(); env.rollout_random(6); env.reset(done_only=True)
-    rows, runs, used = env.afterstates_distinct()
-    vk = vk_mod.ValueKernel(net)
-    vals = vk.values(rows, used.reshape(1))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(20):
-        vk.values(rows, used.reshape(1), out=vals)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    R = int(used)
-    flops = 2.0 * R * (16 * 128 + 3 * 128 * 128 + 128)
-    out["value_rows_kernel"] = {"ms": ms, "rows": R, "rows_per_s": R / (ms * 1e-3), "TFLOPs": flops / (ms * 1e-3) / 1e12,
-                                "note": "tpl_value_rows alone: tcgen05 128x128x16 bf16 MMAs, weights + activations on chip; FLOPs counted as "
-                                        "2 * rows * (16*128 + 3*128*128 + 128)"}
-    return out
+    """BASELINE configs[3]: the DQN afterstate-value loop (model/train.py's constants) driving 65 536 GPU envs -- measured by
+    scripts/dqn_bench.py in a FRESH process on the same GPU: capturing the optimiser block into a CUDA graph empties the caching
+    allocator, which inside this process (gigabytes of cached blocks from the legs above) costs seconds of the timed run."""
+    import subprocess
+    env = dict(os.environ)
+    env.setdefault("CUDA_VISIBLE_DEVICES", str(dev.index or 0))           # the same GPU as this process
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dqn_bench.py")], env=env, capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        return {"error": r.stderr[-400:]}
+    return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
 
 
 def main():

@@ -49,7 +49,13 @@ constexpr int ACT_BYTES = TILE_ROWS * KAUG * 2;
 constexpr int GROUP_BYTES = 4096 + ACT_BYTES;
 constexpr int OFF_BAR = OFF_A0 + GROUPS * GROUP_BYTES;       // 2 mbarriers + the TMEM base address
 constexpr int SMEM_BYTES = OFF_BAR + 32;
-constexpr int TMEM_COLS = 512;                   // per group 128 accumulator columns + 16 for the last layer, at a 256-column pitch
+constexpr int TMEM_COLS = 512;                   // two groups at a 256-column pitch:
+constexpr int TM_D = 0;                          //   128 accumulator columns
+constexpr int TM_A = 128;                        //   the next layer's A operand: 144 bf16 per row = 72 columns (TPL_VALUE_A_TMEM)
+constexpr int TM_OUT = 200;                      //   16 columns for the last layer
+#ifndef TPL_VALUE_A_TMEM
+#define TPL_VALUE_A_TMEM 1                       // activations go back into tensor memory (the MMA's A operand may live there), not through
+#endif                                           // shared memory: the epilogue's 32 KB of shared-memory stores and the MMA's re-read of them drop out
 
 // canonical K-major, no swizzle: element (row, k) of a [rows x K] bf16 tile
 __host__ __device__ constexpr uint32_t canon_off(uint32_t row, uint32_t k, uint32_t K) {
@@ -107,6 +113,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with the A operand in tensor memory (lane = row, two bf16 per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar_saddr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_saddr) : "memory");
 }
@@ -149,6 +161,22 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[N]) {
 #pragma unroll
     for (int j = 0; j < N; ++j) asm volatile("" : "+r"(v[j]));
 }
+// registers -> 32 / 8 consecutive columns of this thread's TMEM lane (warp-collective); tmem_st_wait() completes them
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                    "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                    "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&p);
@@ -190,26 +218,51 @@ value_rows_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict_
     }
     uint8_t *a0 = smem + OFF_A0 + g * GROUP_BYTES, *act = a0 + 4096;
     const uint32_t my_a0 = canon_off((uint32_t)tg, 0, 16), my_act = canon_off((uint32_t)tg, 0, KAUG);
+#if !TPL_VALUE_A_TMEM
     // the bias K-step of this row of the activation tile, written once: (1, 0, ..., 0)
     *reinterpret_cast<uint4 *>(act + my_act + (HID / 8) * 128u) = make_uint4(0x00003F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4 *>(act + my_act + (HID / 8 + 1) * 128u) = make_uint4(0u, 0u, 0u, 0u);
-    proxy_fence();                                // weights and bias columns were written through the generic proxy, the MMAs read through the async one
+#endif
+    proxy_fence();                                // weights (and bias columns) were written through the generic proxy, the MMAs read through the async one
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot + (uint32_t)g * 256u;              // this group's accumulators: 128 lanes x (128 + 16) columns
-    const uint32_t tmem_mine = tmem_d + ((uint32_t)(wq * 32) << 16);      // the 32 lanes this warp may read
+    const uint32_t tmem_d = *tmem_slot + (uint32_t)g * 256u;              // this group's tensor-memory columns (see TM_*)
+    const uint32_t tmem_mine = tmem_d + ((uint32_t)(wq * 32) << 16);      // the 32 lanes this warp may read and write
+#if TPL_VALUE_A_TMEM
+    {   // the bias K-step of this row of the A operand, written once: (1, 0, ..., 0) as bf16 pairs
+        const uint32_t ones[8] = {0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(tmem_mine + TM_A + HID / 2, ones);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+#endif
     const float *B = reinterpret_cast<const float *>(smem + OFF_B);
     const float sc0 = B[0], sc1 = B[1], sc2 = B[2], sc3 = B[3];
     const uint32_t nrows = count ? min(*count, nrows_max) : nrows_max;
     const uint32_t ntiles = (nrows + TILE_ROWS - 1) / TILE_ROWS;
     uint32_t parity = 0;
     const uint32_t abase = smem_u32(act);
+#ifdef TPL_VALUE_TRACE          // developer aid: cycle stamps of CTA 0 / group 0 / thread 0 into the unused tail of `values`
+    float *trace = values + (nrows_max - 4096u);
+    int tr = 0;
+    long long tlast = clock64();
+#define TPL_TR(tag) if (blockIdx.x == 0 && tid == 0 && tr < 4000) { const long long now_ = clock64(); trace[tr++] = (float)(tag); trace[tr++] = (float)(now_ - tlast); tlast = now_; }
+#else
+#define TPL_TR(tag)
+#endif
 
-    for (uint32_t tile = blockIdx.x * GROUPS + g; tile < ntiles; tile += gridDim.x * GROUPS) {
+    const uint32_t tile0 = blockIdx.x * GROUPS + g, tstep = gridDim.x * GROUPS;
+    // this thread's feature word of the NEXT tile is loaded a tile ahead: the DRAM round trip is off the per-tile critical path
+    uint32_t w_next = (tile0 < ntiles && tile0 * TILE_ROWS + (uint32_t)tg < nrows) ? rows[tile0 * TILE_ROWS + (uint32_t)tg] : 0u;
+    for (uint32_t tile = tile0; tile < ntiles; tile += tstep) {
         const uint32_t row = tile * TILE_ROWS + (uint32_t)tg;
         {   // input tile: (rows cleared, holes, bumpiness, aggregate height) * scale, then the constant 1 of the first bias
-            const uint32_t w = row < nrows ? rows[row] : 0u;
+            const uint32_t w = w_next;
+            const uint32_t row2 = row + tstep * TILE_ROWS;
+            w_next = (tile + tstep < ntiles && row2 < nrows) ? rows[row2] : 0u;
             const float f0 = (float)(w & 7u) * sc0, f1 = (float)((w >> 8) & 0xFFu) * sc1, f2 = (float)((w >> 16) & 0xFFu) * sc2,
                         f3 = (float)(w >> 24) * sc3;
             *reinterpret_cast<uint4 *>(a0 + my_a0) = make_uint4(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3), pack_bf16x2(1.0f, 0.0f), 0u);
@@ -219,48 +272,64 @@ value_rows_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict_
         group_sync(g);
         if (tg == 0) {                            // layer 1: one 128 x 128 x 16 instruction
             tc_fence_after();
-            umma_f16(tmem_d, umma_desc(smem_u32(a0), 128, 256), umma_desc(smem_u32(smem + OFF_W1), 128, 256), IDESC_HID, 0u);
+            umma_f16(tmem_d + TM_D, umma_desc(smem_u32(a0), 128, 256), umma_desc(smem_u32(smem + OFF_W1), 128, 256), IDESC_HID, 0u);
             umma_commit(bar);
         }
 #pragma unroll 1
         for (int layer = 1; layer <= 4; ++layer) {
+            TPL_TR(1)
             mbar_wait(bar, parity); parity ^= 1u;
+            TPL_TR(2)
             tc_fence_after();
             // epilogue of a hidden layer: accumulator -> ReLU -> bf16 -> the next MMA's A operand (canonical layout: 8 columns =
             // one 16-byte chunk); the bias came in through the constant-1 column, so there is one instruction per two elements
             {
                 uint32_t v[HID];                  // the whole row of the accumulator: four loads in flight, ONE wait
 #pragma unroll
-                for (int c0 = 0; c0 < HID; c0 += 32) tmem_ld32_issue(tmem_mine + (uint32_t)c0, v + c0);
+                for (int c0 = 0; c0 < HID; c0 += 32) tmem_ld32_issue(tmem_mine + TM_D + (uint32_t)c0, v + c0);
                 tmem_ld_wait(v);
+                TPL_TR(3)
+#if TPL_VALUE_A_TMEM
+                uint32_t a[HID / 2];              // ReLU + bf16, two activations per 32-bit tensor-memory column
+#pragma unroll
+                for (int q = 0; q < HID / 2; ++q) a[q] = relu_pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                tmem_st32(tmem_mine + TM_A, a);
+                tmem_st32(tmem_mine + TM_A + 32, a + 32);
+                tmem_st_wait();
+                TPL_TR(4)
+#else
 #pragma unroll
                 for (int q = 0; q < HID / 8; ++q)
                     *reinterpret_cast<uint4 *>(act + my_act + (uint32_t)q * 128u) =
                         make_uint4(relu_pack_bf16x2(v[8 * q], v[8 * q + 1]), relu_pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    relu_pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), relu_pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                proxy_fence();                    // activations visible to the tensor core's shared-memory reads
+#endif
             }
-            tc_fence_before();                    // this thread's tensor-memory reads are done before anyone overwrites the accumulator
-            proxy_fence();                        // activations visible to the tensor core's shared-memory reads
+            tc_fence_before();                    // this thread's tensor-memory accesses are done before the next MMAs touch the same columns
             group_sync(g);
+            TPL_TR(5)
             if (tg == 0) {
                 tc_fence_after();
-                if (layer < 4) {                  // hidden layer: 128 x 128 x 144 = nine K-steps (the ninth adds the bias)
-                    const uint32_t wbase = smem_u32(smem + OFF_W2 + (layer - 1) * W_BYTES);
+                // hidden layer: 128 x 128 x 144 = nine K-steps (the ninth adds the bias); last layer: 128 x 16 x 144 into its own columns
+                const uint32_t wbase = smem_u32(smem + (layer < 4 ? OFF_W2 + (layer - 1) * W_BYTES : OFF_W5));
+                const uint32_t dcol = tmem_d + (layer < 4 ? TM_D : TM_OUT), idesc = layer < 4 ? IDESC_HID : IDESC_OUT;
 #pragma unroll
-                    for (uint32_t k = 0; k < KAUG / 16; ++k)
-                        umma_f16(tmem_d, umma_desc(abase + k * 256u, 128, KAUG * 16), umma_desc(wbase + k * 256u, 128, KAUG * 16), IDESC_HID, k);
-                } else {                          // last layer: 128 x 16 x 144 into its own accumulator columns
-                    const uint32_t wbase = smem_u32(smem + OFF_W5);
-#pragma unroll
-                    for (uint32_t k = 0; k < KAUG / 16; ++k)
-                        umma_f16(tmem_d + HID, umma_desc(abase + k * 256u, 128, KAUG * 16), umma_desc(wbase + k * 256u, 128, KAUG * 16), IDESC_OUT, k);
+                for (uint32_t k = 0; k < KAUG / 16; ++k) {
+#if TPL_VALUE_A_TMEM
+                    umma_f16_ts(dcol, tmem_d + TM_A + k * 8u, umma_desc(wbase + k * 256u, 128, KAUG * 16), idesc, k);
+#else
+                    umma_f16(dcol, umma_desc(abase + k * 256u, 128, KAUG * 16), umma_desc(wbase + k * 256u, 128, KAUG * 16), idesc, k);
+#endif
                 }
                 umma_commit(bar);
             }
+            TPL_TR(6)
         }
         mbar_wait(bar, parity); parity ^= 1u;
+        TPL_TR(7)
         tc_fence_after();
-        const float value = __uint_as_float(tmem_ld1(tmem_mine + HID));          // column 0 of the last layer's accumulator
+        const float value = __uint_as_float(tmem_ld1(tmem_mine + TM_OUT));       // column 0 of the last layer's accumulator
         if (row < nrows) values[row] = value;
         tc_fence_before();
         group_sync(g);                            // every lane has read its value before the next tile's MMAs run

@@ -50,9 +50,12 @@ class ValueKernel:
         n = self.net
         ps = [n.layer1.weight, n.layer1.bias, n.layer2.weight, n.layer2.bias, n.layer3.weight, n.layer3.bias,
               n.layer4.weight, n.layer4.bias, n.layer5.weight, n.layer5.bias]
-        ps = [p.detach().to(torch.float32).contiguous() for p in ps]
-        self._call(self._L.tpl_value_pack, "tpl_value_pack", *[_ptr(p) for p in ps], ctypes.cast(self._scale, ctypes.c_void_p),
-                   _ptr(self.blob), self._stream())
+        if all(p.dtype == torch.float32 and p.is_contiguous() for p in ps):       # the usual case: the optimiser updates them in place
+            ptrs = [ctypes.c_void_p(p.data_ptr()) for p in ps]
+        else:
+            self._keep = [p.detach().to(torch.float32).contiguous() for p in ps]
+            ptrs = [_ptr(p) for p in self._keep]
+        self._call(self._L.tpl_value_pack, "tpl_value_pack", *ptrs, ctypes.cast(self._scale, ctypes.c_void_p), _ptr(self.blob), self._stream())
 
     def values(self, rows: torch.Tensor, count: torch.Tensor = None, out: torch.Tensor = None) -> torch.Tensor:
         """rows: int32/uint32 CUDA tensor of feature words (distinct-placements form); count: optional 0-d / 1-element int32
