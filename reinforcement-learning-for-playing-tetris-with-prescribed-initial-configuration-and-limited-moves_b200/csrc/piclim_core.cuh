@@ -114,7 +114,14 @@ constexpr OrientTable make_table() {
     return t;
 }
 #undef TPL_O
-__constant__ OrientTable c_orient = make_table();
+#ifdef TPL_HOST_EMUL
+static const OrientTable c_orient = make_table();
+#else
+// In global memory, not __constant__: its only reader is the per-CTA copy into shared memory, one 16-byte chunk per thread, i.e.
+// 32 different addresses per warp, which the constant cache serves one at a time (ncu: 1.9 % of the fused step's warp time sat on
+// that copy); from global memory it is three coalesced 512-byte requests per CTA out of L2.
+__device__ const OrientTable c_orient = make_table();
+#endif
 
 constexpr int TAB_COMPACT4 = 56;     // 28 entries x 2 uint4
 constexpr int TAB_WORDS4 = 56 + 84;  // + 28 wide entries x 3 uint4
@@ -213,6 +220,18 @@ __device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) {
 #else
     int r;
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#endif
+}
+
+// sum over the four bytes of |a - b|, plus c: ONE instruction (VABSDIFF4.U8.ACC with a live accumulator).  Written as
+// `__vsadu4(a, b) + c` the accumulator operand stays zero and ptxas appends a separate add.
+__device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef TPL_HOST_EMUL
+    return __vsadu4(a, b) + c;
+#else
+    uint32_t r;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 #endif
 }

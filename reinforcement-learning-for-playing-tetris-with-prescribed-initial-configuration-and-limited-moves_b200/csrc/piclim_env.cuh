@@ -40,9 +40,17 @@ __device__ __forceinline__ void pack_queue(const uint8_t *pieces, int np, uint32
 // ---------------------------------------------------------------------------------------------
 // reset: install pool record k with ctor-fresh counters (game/tetris.py:447 and :149-151)
 // ---------------------------------------------------------------------------------------------
+// (install_record: the four chunks of the pool record come from the caller -- the fused step has them copied into shared
+// memory a whole tile ahead, see step_observe_kernel)
+__device__ __forceinline__ void install_record(Env &e, const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint64_t seed,
+                                               uint64_t env, uint32_t episode, int gen_count);
 __device__ __forceinline__ void install_config(Env &e, const uint4 *__restrict__ pool, uint32_t k, uint64_t seed,
                                                uint64_t env, uint32_t episode, int gen_count) {
     const uint4 a = pool[4 * (size_t)k], b = pool[4 * (size_t)k + 1], c = pool[4 * (size_t)k + 2], d = pool[4 * (size_t)k + 3];
+    install_record(e, a, b, c, d, seed, env, episode, gen_count);
+}
+__device__ __forceinline__ void install_record(Env &e, const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint64_t seed,
+                                               uint64_t env, uint32_t episode, int gen_count) {
     unpack_env(a, b, c, d, e);
     e.lines = 0; e.moves = 0; e.state = S_RUNNING; e.head = 0; e.qblock = 0;
     if (gen_count > 0) {                      // (more than 42: the first block now, the rest by refill_queue as the episode goes on)
@@ -74,7 +82,7 @@ __device__ __forceinline__ uint32_t step_env(Env &e, const uint4 *tab, uint32_t 
 //
 // Fast path (no row clears), per slot, all on packed bytes / halfwords:
 //   y      = max_j(H[c+j] - bo_j)                          hard drop in height form (:424-433)
-//   full   = A[c] & ((col[c+j] + cb_j << y) for j<4) & (hm << y)   rows of the piece that become full (:382-386)
+//   full   = A[c] & ((col[c+j] + cb_j << y) for j<4)       rows of the piece that become full (:382-386); A excludes old full rows
 //   N      = y + to_j on the columns the shape covers, H[c+j] elsewhere (one byte-wise IMAD + one LOP3 select)
 //   agg'   = agg + sum_j (N_j - H_j)                        one VABSDIFF4.U8.ACC
 //   bump'  = bump - old pairs + new pairs                   one VABSDIFF4.U8.ACC + one VABSDIFF
@@ -96,7 +104,7 @@ __device__ __forceinline__ uint32_t window_pairs(uint32_t N4, uint32_t hprev, ui
     // X = (H[c-1], n0, n1, n2): for the interior columns that is N4 * 256 + H[c-1], one IMAD on the FMA pipe
     const uint32_t X = (C >= 1 && C <= 7) ? mad_fma_pipe(N4, 256u, hprev) : __byte_perm(N4, hprev, sel_x(C));
     const uint32_t Y = (C <= 6) ? N4 : __byte_perm(N4, 0u, sel_y(C));
-    uint32_t s = __vsadu4(X, Y) + acc;
+    uint32_t s = vsad4_acc(X, Y, acc);
     if (C + 4 <= 9) s = __sad((int)(N4 >> 24), (int)hnext, s);
     return s;
 }
@@ -107,7 +115,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                                           const uint32_t (&A)[COLS], const uint32_t (&Bb)[COLS], uint32_t agg, uint32_t K, uint32_t U,
                                           uint32_t flN, uint32_t flT, int w,
                                           int nb0, int nb1, int nb2, int nb3, uint32_t cb0, uint32_t cb1, uint32_t cb2, uint32_t cb3,
-                                          uint32_t TO4, uint32_t cover, uint32_t hm, int thr, uint32_t one,
+                                          uint32_t TO4, uint32_t cover, int thr, uint32_t one,
                                           uint32_t &word, uint32_t &fl, bool &pend, uint32_t &pmask, uint32_t &nsmask, int cmax_warp) {
     // Distinct-placements form: alias slots are not stored at all, so a column that no distinct placement of ANY piece reaches in
     // this rotation is skipped outright -- rotation 0: column 9; rotation 2: columns 8 and 9 (the only two-wide shape there is O,
@@ -141,11 +149,14 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     const bool top = y > thr;
     const uint32_t pw = 1u << y;
     // the piece lands on empty cells, so `column | piece image` is `column + piece image`: one IMAD per window column
-    const uint32_t full = A[C] & mul_fma_pipe(hm, pw) & mad_fma_pipe(cb0, pw, col[C]) & mad_fma_pipe(cb1, pw, col[C + 1]) &
+    // No mask for the piece's rows (:382-383) is needed: A excludes the rows that were full before the placement (see
+    // afterstates_env_impl), every row the piece spans receives at least one of its cells -- so it was not full before -- and
+    // no other row changes: the rows that are full now and were not before ARE the completed rows of the piece.
+    const uint32_t full = A[C] & mad_fma_pipe(cb0, pw, col[C]) & mad_fma_pipe(cb1, pw, col[C + 1]) &
                           mad_fma_pipe(cb2, pw, col[C + 2]) & mad_fma_pipe(cb3, pw, col[C + 3]);
     // new heights of the window as bytes: y + to_j where the shape covers the column, the old height elsewhere
     const uint32_t N4 = (mad_fma_pipe((uint32_t)y, 0x01010101u, TO4) & cover) | (Hw[C] & ~cover);
-    const uint32_t agg2 = __vsadu4(N4, Hw[C]) + agg;
+    const uint32_t agg2 = vsad4_acc(N4, Hw[C], agg);
     const uint32_t b2 = window_pairs<C>(N4, (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], Bb[C]);
     uint32_t wnew = agg2 * 0x01000100u + K;
     wnew = b2 * 0x10000u + wnew;
@@ -171,7 +182,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             // that is both (a row of an overflowing piece completes -- very rare) is deferred too; resolve_slot handles it.
             const bool pnew = full != 0u;
             if (!pnew) sink.put_packed_col(C, wnew);
-            if (top) sink.put_packed_col(C, U);
+            if (top) sink.put_packed_col_again(C, U);   // (a second, separately predicated store -- see GlobalSink)
             if (pnew) { pmask |= 1u << C; nsmask |= 1u << C; }
             pend = pnew && !top;
         } else {
@@ -289,8 +300,14 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     for (int k = 0; k < COLS; ++k) pre[k + 1] = pre[k] & col[k];
 #pragma unroll
     for (int k = COLS - 1; k >= 0; --k) suf[k] = suf[k + 1] & col[k];
+    // ... and not among the rows that are full already (pre[10]; an untouched full row stays, :382-383, and must not count)
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) A[c] = pre[c] & suf[c + 4 < 10 ? c + 4 : 10];
+    for (int c = 0; c < COLS; ++c) {
+        A[c] = pre[c] & suf[c + 4 < 10 ? c + 4 : 10] & ~pre[10];
+#if defined(__CUDA_ARCH__) && !defined(TPL_NO_PIN_A)
+        asm volatile("" : "+r"(A[c]));      // keep the ten masks in registers: re-deriving them from pre / suf costs a LOP3 per slot
+#endif
+    }
 
     const uint32_t U = ((agg - cells) << 8) | (bump << 16) | (agg << 24);   // unchanged board (top-out slots)
     const uint32_t K = 0u - ((cells + 4u) << 8);                             // holes' = agg' - (cells + 4)
@@ -321,7 +338,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
         if constexpr (Sink::RAGGED) sink.begin_rotation_ragged(canon, orient_rot_base(tab[(piece * 4 + r) * 2 + 1]));
         else if constexpr (Sink::PACKED) sink.begin_rotation(r);
 #define TPL_SLOT(C) slot_fast<C, UNIFORM>(sink, r, H, Hw, col, A, Bb, agg, Kr, Ur, flN, flT, w, nb0, nb1, nb2, nb3, cb0, cb1, cb2, cb3, \
-                                 wm.x, wm.y, wm.z, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
+                                 wm.x, wm.y, (int)wm.w, one, word, fl, pend, pmask, nsmask, cmax_warp);
         TPL_SLOT(0) TPL_SLOT(1) TPL_SLOT(2) TPL_SLOT(3) TPL_SLOT(4) TPL_SLOT(5) TPL_SLOT(6) TPL_SLOT(7) TPL_SLOT(8) TPL_SLOT(9)
 #undef TPL_SLOT
         if (canon) pending |= (unsigned long long)pmask << (10 * r);

@@ -14,7 +14,10 @@
 
 namespace tpl {
 
-constexpr int THREADS = 128;
+#ifndef TPL_THREADS
+#define TPL_THREADS 128              // threads per CTA of every kernel here (tuning knob; the launch bounds below assume 128)
+#endif
+constexpr int THREADS = TPL_THREADS;
 
 static thread_local char g_err[256] = "";
 static std::atomic<long long> g_launches{0};
@@ -200,6 +203,16 @@ struct GlobalSink {
 #endif
     }
     __device__ __forceinline__ void put_packed_col(int, uint32_t packed) { *pcol = packed; }
+    // The same address through an opaque copy of the pointer.  `if (!a) *p = x; if (b) *p = y;` on one visible address is fused
+    // into a select, a combined predicate and ONE store -- two instructions on the ALU pipe, the pipe that bounds the
+    // enumeration -- while two predicated stores cost one more issue slot on the load/store pipe, which has room.
+    __device__ __forceinline__ void put_packed_col_again(int, uint32_t packed) {
+        uint32_t *p2 = pcol;
+#ifdef __CUDA_ARCH__
+        asm("" : "+l"(p2));
+#endif
+        *p2 = packed;
+    }
     // pcol += n words.  64-bit form: ONE multiply-add by `one` (with an immediate multiplier ptxas strength-reduces it to a
     // LEA / LEA.HI.X pair on the ALU pipe); ptxas turns it into IADD3 + IMAD.X.
     __device__ __forceinline__ void next_col() {
@@ -282,7 +295,8 @@ __device__ __forceinline__ typename ResolveSink<MODE>::type make_resolve_sink(ui
 // cover each other's load latency.
 constexpr int WQ_ENVS = 64;          // env entries: < 32 live after a resolve + <= 32 new per tile
 #ifndef TPL_WQ_ITEMS
-#define TPL_WQ_ITEMS 512             // (-DTPL_WQ_ITEMS=40 makes the overflow path below run all the time: used once to validate it)
+#define TPL_WQ_ITEMS 128             // (-DTPL_WQ_ITEMS=40 makes the overflow path below run all the time: used once to validate it;
+                                     //  128 instead of 512 keeps the distinct-form kernels at four CTAs per SM next to the pool-record stage)
 #endif
 constexpr int WQ_ITEMS = TPL_WQ_ITEMS;   // deferred slots (>= 40); a lane whose slots do not fit resolves them itself (never seen in practice)
 static_assert(WQ_ITEMS >= 40, "room for the < 32 live items plus at least a few new ones");
@@ -317,6 +331,20 @@ __device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, c
     }
 }
 
+// Exclusive prefix sum over the warp of small counts (cnt <= 63; top = their warp maximum): one ballot per bit that is set in
+// any count -- independent instructions -- instead of the five dependent shuffle + select + add rounds of the classic scan
+// (ncu: the scan alone held 2 % of all warp time in short-scoreboard stalls; the counts here are almost always 0, 1 or 2).
+__device__ __forceinline__ uint32_t warp_prefix_small(uint32_t cnt, uint32_t top) {
+    const uint32_t lt = (1u << (threadIdx.x & 31u)) - 1u;
+    uint32_t excl = 0u;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        if ((top >> b) == 0u) break;                                   // warp-uniform
+        excl += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, (cnt >> b) & 1u) & lt) << b;
+    }
+    return excl;
+}
+
 // every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer); `i` = env index, or in the
 // distinct-placements form the word offset of the env's run
 template <int MODE>
@@ -325,11 +353,9 @@ __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e,
                                            float4 *ff, int L, uint32_t one) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t cnt = (uint32_t)__popcll(cx.mask);
-    const unsigned have = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
-    if (have == 0u) return;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, cnt);
+    if (top == 0u) return;
+    const uint32_t incl = warp_prefix_small(cnt, top) + cnt;
     const uint32_t room = WQ_ITEMS - (p.tail - p.head);
     const bool fits = incl <= room;                                    // monotone in the lane index
     const unsigned fit = __ballot_sync(0xFFFFFFFFu, cnt != 0u && fits);
@@ -371,13 +397,12 @@ struct RagTile { uint32_t excl, total, tb; };
 // cnt = this lane's run length (0 / 9 / 17 / 34): exclusive prefix over the warp, and one atomicAdd reserving the tile's
 // words (rounded up to 4 so that every tile starts 16-byte aligned); the returned base is only needed after the enumeration
 __device__ __forceinline__ RagTile rag_reserve(uint32_t cnt, uint32_t *cursor) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    // the run lengths are 0, 9, 17 or 34: the prefix is three ballots (independent) instead of a five-round shuffle scan
+    const unsigned b9 = __ballot_sync(0xFFFFFFFFu, cnt == 9u), b17 = __ballot_sync(0xFFFFFFFFu, cnt == 17u), b34 = __ballot_sync(0xFFFFFFFFu, cnt == 34u);
     RagTile t;
-    t.excl = incl - cnt;
-    t.total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    t.excl = 9u * (uint32_t)__popc(b9 & lt) + 17u * (uint32_t)__popc(b17 & lt) + 34u * (uint32_t)__popc(b34 & lt);
+    t.total = 9u * (uint32_t)__popc(b9) + 17u * (uint32_t)__popc(b17) + 34u * (uint32_t)__popc(b34);
     t.tb = 0u;
     if (lane == 0u && t.total) t.tb = atomicAdd(cursor, (t.total + 3u) & ~3u);
     return t;
@@ -445,8 +470,31 @@ __device__ __forceinline__ void stage_take(RecordStage &rs, Env &e) {
     unpack_env(a, b, c, d, e);
 }
 
+// ---- pool-record pipeline: the record a reset of the NEXT tile would install -- a pure function of (seed, env, episode + 1) --
+// is copied global -> shared memory with cp.async while the current tile is enumerated, like the env records themselves.
+// Why: the gather is L2-resident, yet ncu showed ~1000 cycles of long-scoreboard stall per tile where the record was first used
+// (6.8 % of all warp time) although it had been prefetched towards L1 at the top of the tile; loading it into registers ahead
+// of the move shortened the stall but not the step (the loads queue behind the tile's DRAM traffic in the in-order L1, and a
+// dead word of the record made ptxas reuse its register, which then waited for the load: write-after-write).  A whole
+// enumeration (~8000 cycles) of distance costs no registers and removes the stall.
+__device__ __forceinline__ void pool_issue(RecordStage &ps, const uint4 *pool, uint32_t k) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint4 *p = pool + 4 * (size_t)k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ps.chunk[j][lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(p + j) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 #ifndef TPL_AS_MINBLOCKS
 #define TPL_AS_MINBLOCKS 4          // 128 registers per thread: fewer re-materialised operands than the default choice of 96
+#endif
+#ifdef TPL_AS_MAXNREG               // tuning knob: an explicit register cap instead of the one the launch bounds imply
+#define TPL_AS_BOUNDS __maxnreg__(TPL_AS_MAXNREG)
+#else
+#define TPL_AS_BOUNDS __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
 #endif
 // piece and run length (distinct placements) of the env's current piece; 7 / 0 when the queue is empty
 __device__ __forceinline__ void current_run(const Env &e, const uint4 *tab, uint32_t &piece, uint32_t &cnt) {
@@ -455,7 +503,7 @@ __device__ __forceinline__ void current_run(const Env &e, const uint4 *tab, uint
 }
 
 template <int MODE, bool P32 = false>
-__global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)
+__global__ void TPL_AS_BOUNDS
 afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t *__restrict__ words,
                    uint8_t *__restrict__ flags, float4 *__restrict__ ff, int L, int M, uint32_t one,
                    uint32_t *__restrict__ runs, uint32_t run_base, uint32_t *cursor, uint32_t *cursor_clear) {
@@ -546,6 +594,7 @@ struct TileSink {                                          // packed words at th
     uint32_t *orot;
     __device__ __forceinline__ void begin_rotation(int r) { orot = out + r * 10 * TILE; }
     __device__ __forceinline__ void put_packed_col(int c, uint32_t packed) { orot[c * TILE] = packed; }
+    __device__ __forceinline__ void put_packed_col_again(int c, uint32_t packed) { orot[c * TILE] = packed; }
     __device__ __forceinline__ void next_col() {}
     __device__ __forceinline__ void put_packed(int slot, uint32_t packed) { out[slot * TILE] = packed; }
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) { out[slot * TILE] = word | (fl << 3); }
@@ -662,7 +711,7 @@ afterstates_sorted_kernel(const uint4 *__restrict__ st, int64_t stride, int n, u
 // integer work of the 40-slot enumeration (the three separate kernels read the state 2.25 times and write it twice).
 // =================================================================================================
 template <int MODE, bool P32 = false>
-__global__ void __launch_bounds__(THREADS, TPL_AS_MINBLOCKS)      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
+__global__ void TPL_AS_BOUNDS      // 128 registers: unconstrained, ptxas takes 166 and occupancy drops to 12 warps/SM
 step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, const uint8_t *__restrict__ loc,
                     int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats,
                     const uint4 *__restrict__ pool, int K, uint32_t *episode, uint32_t *tstep, uint64_t seed, uint64_t env_base, int gen_count,
@@ -674,38 +723,40 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
     load_table(s_tab);
-    __shared__ RecordStage s_stage[THREADS / 32];
+    __shared__ RecordStage s_stage[THREADS / 32], s_pstage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
-    RecordStage &rs = s_stage[threadIdx.x >> 5];
+    RecordStage &rs = s_stage[threadIdx.x >> 5], &pstage = s_pstage[threadIdx.x >> 5];
     uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
     if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
     int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
-    // the next tile's action and episode number ride in three registers; its records in shared memory (stage_issue)
-    uint32_t nrot = 0, nloc = 0, nep = 0;
+    // The next tile's action and episode number ride in three registers, its records in shared memory (stage_issue); the episode
+    // number of the tile after that rides in a fourth, because the pool record of the next tile is requested in the middle of this
+    // one (pool_issue) and the number it is drawn from must have arrived by then.
+    uint32_t nrot = 0, nloc = 0, nep = 0, nep2 = 0;
     if (t < wtiles) {
-        const int64_t i0 = (int64_t)t * 32 + (threadIdx.x & 31);
+        const int64_t i0 = (int64_t)t * 32 + (threadIdx.x & 31), i1 = i0 + (int64_t)wstep * 32;
         stage_issue(rs, st, stride, i0, n);
         if (i0 < n) { nrot = rot[i0]; nloc = loc[i0]; nep = episode ? episode[i0] : 0u; }
+        if (i1 < n) nep2 = episode ? episode[i1] : 0u;
+        if (pool) pool_issue(pstage, pool, config_index(seed, env_base + (uint64_t)(i0 < n ? i0 : (int64_t)n - 1), nep + 1u, K));
     }
     for (; t < wtiles; t += wstep) {                                                                    // warp-uniform trip count
-        const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
+        const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31), i2 = i + (int64_t)wstep * 32;
         PendingCtx cx; cx.mask = 0ull;
         Env e;
         stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
-        const uint32_t arot = nrot, aloc = nloc, ep1 = nep + 1u;
+        const uint32_t arot = nrot, aloc = nloc, ep1 = nep + 1u, ep1_next = nep2 + 1u;
         {
-            const int64_t i2 = i + (int64_t)wstep * 32;
+            const int64_t i3 = i2 + (int64_t)wstep * 32;
             if (t + wstep < wtiles) stage_issue(rs, st, stride, i2, n);
-            if (i2 < n) { nrot = rot[i2]; nloc = loc[i2]; nep = episode ? episode[i2] : 0u; }
+            if (i2 < n) { nrot = rot[i2]; nloc = loc[i2]; }
+            nep = nep2;
+            if (i3 < n) nep2 = episode ? episode[i3] : 0u;
         }
         if (i < n) {
-            // Which pool record a reset would install depends only on (seed, env, episode + 1): draw it now and pull the record
-            // towards L1, so the reset below -- taken by some lane of almost every warp -- does not wait for an L2 gather.
-            uint32_t kcfg = 0;
-            if (pool) { kcfg = config_index(seed, env_base + (uint64_t)i, ep1, K); prefetch_l1(pool + 4 * (size_t)kcfg); }
             const uint32_t was = e.state;
             int k; bool changed;
             const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
@@ -721,7 +772,9 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
             else if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {       // TPL_RESET_DONE semantics
                 if (episode) episode[i] = ep1;
                 if (tstep) tstep[i] = 0u;                                           // a new episode: the action stream of the rollouts restarts
-                install_config(e, pool, kcfg, seed, env_base + (uint64_t)i, ep1, gen_count);
+                const uint32_t lane = threadIdx.x & 31u;                            // (the record landed with this tile's env records)
+                install_record(e, pstage.chunk[0][lane], pstage.chunk[1][lane], pstage.chunk[2][lane], pstage.chunk[3][lane], seed,
+                               env_base + (uint64_t)i, ep1, gen_count);
                 acc[7] += 1;
                 changed = true;
             }
@@ -732,6 +785,9 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
             }
             st[3 * stride + i] = pack_meta(e);
         }
+        // the record the next tile's reset would install: on its way during the enumeration below
+        if (pool && t + wstep < wtiles)
+            pool_issue(pstage, pool, config_index(seed, env_base + (uint64_t)(i2 < n ? i2 : (int64_t)n - 1), ep1_next, K));
         if constexpr (RAG) {
             uint32_t piece = 7u, cnt = 0u;
             if (i < n) current_run(e, s_tab, piece, cnt);
@@ -833,11 +889,10 @@ __device__ __forceinline__ void rollout_greedy_step_pooled(Env &e, uint32_t &ep,
     PendingCtx cx; cx.mask = 0ull;
     if (valid) afterstates_env(e, tab, scr, THREADS, L, M, sink, 0, 4, &cx);
     const uint32_t cnt = (uint32_t)__popcll(cx.mask);
-    if (__ballot_sync(0xFFFFFFFFu, cnt != 0u)) {
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, cnt);
+    if (top) {
+        const uint32_t incl = warp_prefix_small(cnt, top) + cnt;
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
         gp.key[lane] = 0ull;
         if (cnt) {
 #pragma unroll

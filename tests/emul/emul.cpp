@@ -31,6 +31,7 @@ struct PackedRowSink {
     int rot;
     void begin_rotation(int r) { rot = r; }
     void put_packed_col(int c, uint32_t packed) { row[rot * 10 + c] = packed; }
+    void put_packed_col_again(int c, uint32_t packed) { row[rot * 10 + c] = packed; }
     void next_col() {}
     void put_packed(int slot, uint32_t packed) { row[slot] = packed; }
     void put(int slot, uint32_t word, uint32_t fl) { row[slot] = word | (fl << 3); }
