@@ -167,12 +167,12 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
         if (C <= 6) {                                  // every width fits (w <= 4)
             if (!pnew) sink.template put_col<C>(wnew);
             if (top) sink.template put_col<C>(U);
-            if (pnew) pmask |= 1u << C;
+            if (pnew) pmask = mad_fma_pipe(one, 1u << C, pmask);       // (bit C is not set yet: + is |, and the add runs on the FMA pipe)
         } else {
             const bool fits = C + w <= COLS;
             if (fits && !pnew) sink.template put_col<C>(wnew);
             if (fits && top) sink.template put_col<C>(U);
-            if (fits && pnew) pmask |= 1u << C;
+            if (fits && pnew) pmask = mad_fma_pipe(one, 1u << C, pmask);
         }
     } else if constexpr (Sink::PACKED) {
         // compact form: the flags ride in byte 0 (K and U already carry flN << 3 / flT << 3 for this rotation)
@@ -183,7 +183,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             const bool pnew = full != 0u;
             if (!pnew) sink.put_packed_col(C, wnew);
             if (top) sink.put_packed_col_again(C, U);   // (a second, separately predicated store -- see GlobalSink)
-            if (pnew) { pmask |= 1u << C; nsmask |= 1u << C; }
+            if (pnew) { pmask = mad_fma_pipe(one, 1u << C, pmask); nsmask |= 1u << C; }
             pend = pnew && !top;
         } else {
             const bool pnew = !top && full != 0u;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
                 word = fits ? wnew : (word | (F_ALIAS << 3));
                 pend = fits ? pnew : pend;
             }
-            if (pend && (C == 6 || C + w <= COLS)) pmask |= 1u << C;
+            if (pend && (C == 6 || C + w <= COLS)) pmask = mad_fma_pipe(one, 1u << C, pmask);
             if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
         }
         sink.next_col();
@@ -210,7 +210,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             fl = fits ? fnew : (fl | F_ALIAS);
             pend = fits ? pnew : pend;
         }
-        if (pend && (C <= 6 || C + w <= COLS)) pmask |= 1u << C;
+        if (pend && (C <= 6 || C + w <= COLS)) pmask = mad_fma_pipe(one, 1u << C, pmask);
         if (!pend) sink.put(r * 10 + C, word, fl); else nsmask |= 1u << C;
     }
 }

@@ -37,6 +37,15 @@ const char *last_error() { return g_err; }
 
 #define TPL_SCRATCH __shared__ uint32_t s_scr[SCR_ROWS * THREADS]; uint32_t *scr = s_scr + threadIdx.x
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------------
+// The persistent kernels are launched with the programmatic-stream-serialization attribute (launch_pdl below).  Each CTA lets
+// the NEXT kernel of the stream start launching right away (pdl_trigger) -- its CTAs become resident as the CTAs of this grid
+// retire, copy the orientation table and set up their shared memory during this grid's tail -- and touches nothing a previous
+// kernel may still be producing before pdl_wait(), which returns once every grid this one depends on has completed and its
+// memory is visible.  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void load_table(uint4 *s_tab) {
     for (int t = threadIdx.x; t < TAB_WORDS4; t += blockDim.x) s_tab[t] = reinterpret_cast<const uint4 *>(&c_orient)[t];
     __syncthreads();
@@ -146,7 +155,9 @@ step_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict__ rot, c
             int8_t *dlines, uint8_t *flags, int8_t *sto, unsigned long long *stats, int L, int M) {
     __shared__ uint4 s_tab[TAB_WORDS4];
     TPL_SCRATCH;
+    pdl_trigger();
     load_table(s_tab);
+    pdl_wait();
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // software pipeline: the next env's record and action are in flight while the current move is computed
     const int64_t stepn = (int64_t)gridDim.x * THREADS;
@@ -512,11 +523,13 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
+    pdl_trigger();
     load_table(s_tab);
     __shared__ RecordStage s_stage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
     RecordStage &rs = s_stage[threadIdx.x >> 5];
     uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
+    pdl_wait();                                                      // nothing above reads or writes what another kernel produces
     if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
@@ -722,11 +735,13 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
     __shared__ uint4 s_tab[TAB_WORDS4];
     __shared__ WarpQueue s_wq[THREADS / 32];
     TPL_SCRATCH;
+    pdl_trigger();
     load_table(s_tab);
     __shared__ RecordStage s_stage[THREADS / 32], s_pstage[THREADS / 32];
     WarpQueue &q = s_wq[threadIdx.x >> 5];
     RecordStage &rs = s_stage[threadIdx.x >> 5], &pstage = s_pstage[threadIdx.x >> 5];
     uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
+    pdl_wait();                                                      // nothing above reads or writes what another kernel produces
     if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1019,6 +1034,21 @@ static bool one_window(const void *feats, int n) {
     return !disabled && (a >> 32) == (b >> 32);
 }
 
+// Launch with programmatic dependent launch allowed (see pdl_trigger / pdl_wait): the prologue of this kernel may overlap the
+// tail of the previous kernel in the stream.  TPL_NO_PDL=1 (read once per process) launches plainly, for comparisons.
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, size_t dyn_smem, cudaStream_t s, Args... args) {
+    static int disabled = -1;
+    if (disabled < 0) { const char *v = getenv("TPL_NO_PDL"); disabled = (v && v[0] == '1') ? 1 : 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = disabled ? 0u : 1u;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);       // (errors surface through check_launch -> cudaGetLastError)
+}
+
 static unsigned grid_persistent(int n, int blocks_per_sm) {
     const int sms = sm_count();
     if (blocks_per_sm <= 0) blocks_per_sm = 16;
@@ -1067,17 +1097,17 @@ static int step_observe_impl(const char *who, void *state, int64_t plane_stride,
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<4>, THREADS, RAG_SMEM_BYTES) != cudaSuccess || so_blocks_per_sm <= 0)
                 so_blocks_per_sm = 4;
         }
-        step_observe_kernel<4><<<grid_persistent(n, so_blocks_per_sm), THREADS, RAG_SMEM_BYTES, s>>>(
-            sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, seed, env_base, gen_count, rows, nullptr, nullptr, L, M, 1u,
-            runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
+        launch_pdl(step_observe_kernel<4>, grid_persistent(n, so_blocks_per_sm), RAG_SMEM_BYTES, s,
+                   sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, seed, env_base, gen_count, rows, nullptr, nullptr, L, M, 1u,
+                   runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
         return check_launch(who);
     }
     if (!so_blocks_per_sm &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&so_blocks_per_sm, step_observe_kernel<0>, THREADS, 0) != cudaSuccess || so_blocks_per_sm <= 0))
         so_blocks_per_sm = 4;
     const unsigned g = grid_persistent(n, so_blocks_per_sm);
-#define TPL_SO(...) step_observe_kernel<__VA_ARGS__><<<g, THREADS, 0, s>>>(sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, \
-                                                                    seed, env_base, gen_count, w, aflags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr)
+#define TPL_SO(...) launch_pdl(step_observe_kernel<__VA_ARGS__>, g, 0, s, sp, plane_stride, n, rot, loc, dlines, flags, st, sq, pp, K, episode, tstep, \
+                               seed, env_base, gen_count, w, aflags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr)
     if (feats && !aflags && one_window(feats, n)) TPL_SO(0, true);
     else if (feats && !aflags) TPL_SO(0);
     else if (feats && !feats_f32) TPL_SO(1);
@@ -1138,8 +1168,8 @@ int tpl_step(void *state, int64_t plane_stride, int n, const uint8_t *rot, const
     if (!step_blocks_per_sm &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&step_blocks_per_sm, step_kernel, THREADS, 0) != cudaSuccess || step_blocks_per_sm <= 0))
         step_blocks_per_sm = 8;
-    step_kernel<<<grid_persistent(n, step_blocks_per_sm), THREADS, 0, (cudaStream_t)stream>>>((uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
-                                                                    (unsigned long long *)stats, L, M);
+    launch_pdl(step_kernel, grid_persistent(n, step_blocks_per_sm), 0, (cudaStream_t)stream, (uint4 *)state, plane_stride, n, rot, loc, dlines, flags, st,
+               (unsigned long long *)stats, L, M);
     return check_launch("tpl_step");
 }
 
@@ -1176,11 +1206,11 @@ int tpl_afterstates(const void *state, int64_t plane_stride, int n, uint8_t *fea
         else afterstates_split_kernel<3><<<g4, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u);
         return check_launch("tpl_afterstates(split)");
     }
-    if (feats && !flags && one_window(feats, n)) afterstates_kernel<0, true><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
-    else if (feats && !flags) afterstates_kernel<0><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
-    else if (feats && !feats_f32) afterstates_kernel<1><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
-    else if (!feats) afterstates_kernel<2><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
-    else afterstates_kernel<3><<<g, THREADS, 0, s>>>(st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    if (feats && !flags && one_window(feats, n)) launch_pdl(afterstates_kernel<0, true>, g, 0, s, st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (feats && !flags) launch_pdl(afterstates_kernel<0>, g, 0, s, st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (feats && !feats_f32) launch_pdl(afterstates_kernel<1>, g, 0, s, st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else if (!feats) launch_pdl(afterstates_kernel<2>, g, 0, s, st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
+    else launch_pdl(afterstates_kernel<3>, g, 0, s, st, plane_stride, n, w, flags, f, L, M, 1u, nullptr, 0u, nullptr, nullptr);
     return check_launch("tpl_afterstates");
 }
 
@@ -1213,8 +1243,8 @@ int tpl_afterstates_distinct(const void *state, int64_t plane_stride, int n, uin
         rc = allow_rag_smem(afterstates_kernel<4>, "tpl_afterstates_distinct"); if (rc) return rc;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, afterstates_kernel<4>, THREADS, RAG_SMEM_BYTES) != cudaSuccess || bps <= 0) bps = 4;
     }
-    afterstates_kernel<4><<<grid_persistent(n, bps), THREADS, RAG_SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const uint4 *)state, plane_stride, n, rows, nullptr, nullptr, L, M, 1u, runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
+    launch_pdl(afterstates_kernel<4>, grid_persistent(n, bps), RAG_SMEM_BYTES, (cudaStream_t)stream,
+               (const uint4 *)state, plane_stride, n, rows, nullptr, nullptr, L, M, 1u, runs, run_base, cursor2 + phase, cursor2 + (phase ^ 1));
     return check_launch("tpl_afterstates_distinct");
 }
 
