@@ -285,14 +285,21 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     Hw[1] = __byte_perm(HB0, HB1, 0x4321); Hw[2] = __byte_perm(HB0, HB1, 0x5432); Hw[3] = __byte_perm(HB0, HB1, 0x6543);
     Hw[5] = __byte_perm(HB1, HB2, 0x4321); Hw[6] = __byte_perm(HB1, HB2, 0x5432); Hw[7] = __byte_perm(HB1, HB2, 0x6543);
     Hw[9] = HB2 >> 8;
-    const uint32_t agg = __vsadu4(HB0, 0u) + __vsadu4(HB1, 0u) + __vsadu4(HB2, 0u);
-    const uint32_t bump = __vsadu4(Hw[0], Hw[1]) + __vsadu4(Hw[4], Hw[5]) + (uint32_t)__sad(H[8], H[9], 0u);
+    const uint32_t agg = vsad4_acc(HB2, 0u, vsad4_acc(HB1, 0u, vsad4_acc(HB0, 0u, 0u)));
+    // Running sums of the height steps: P[k] = sum over j < k of |H[j] - H[j+1]| (one abs-diff-accumulate each), so bumpiness = P[9]
+    // and the steps a placement at column c can change -- those between columns c-1 .. c+4 -- are P[min(c+4, 9)] - P[max(c-1, 0)].
+    uint32_t P[COLS];
+    P[0] = 0u;
+#pragma unroll
+    for (int k = 1; k < COLS; ++k) P[k] = (uint32_t)__sad(H[k - 1], H[k], P[k - 1]);
+    const uint32_t bump = P[9];
     uint32_t Bb[COLS];                               // bump minus the pairs a placement at c can change
-    {
-        uint32_t t;
-#define TPL_BB(C) t = window_pairs<C>(Hw[C], (uint32_t)H[C > 0 ? C - 1 : 0], (uint32_t)H[C + 4 <= 13 ? C + 4 : 13], 0u); Bb[C] = bump - t;
-        TPL_BB(0) TPL_BB(1) TPL_BB(2) TPL_BB(3) TPL_BB(4) TPL_BB(5) TPL_BB(6) TPL_BB(7) TPL_BB(8) TPL_BB(9)
-#undef TPL_BB
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+        Bb[c] = bump + P[c > 0 ? c - 1 : 0] - P[c + 4 < 9 ? c + 4 : 9];
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+r"(Bb[c]));     // (kept in registers: re-deriving them from the running sums would cost an add per slot)
+#endif
     }
     uint32_t pre[11], suf[11], A[COLS];              // A[c] = AND of the columns outside [c, c+3]
     pre[0] = COL_FULL; suf[10] = COL_FULL;

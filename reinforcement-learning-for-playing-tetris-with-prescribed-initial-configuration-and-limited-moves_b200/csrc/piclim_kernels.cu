@@ -306,11 +306,11 @@ __device__ __forceinline__ typename ResolveSink<MODE>::type make_resolve_sink(ui
 // cover each other's load latency.
 constexpr int WQ_ENVS = 64;          // env entries: < 32 live after a resolve + <= 32 new per tile
 #ifndef TPL_WQ_ITEMS
-#define TPL_WQ_ITEMS 128             // (-DTPL_WQ_ITEMS=40 makes the overflow path below run all the time: used once to validate it;
+#define TPL_WQ_ITEMS 128             // (-DTPL_WQ_ITEMS=72 makes the wait-for-room path of wq_publish run often: scripts/overflow_check.sh;
                                      //  128 instead of 512 keeps the distinct-form kernels at four CTAs per SM next to the pool-record stage)
 #endif
-constexpr int WQ_ITEMS = TPL_WQ_ITEMS;   // deferred slots (>= 40); a lane whose slots do not fit resolves them itself (never seen in practice)
-static_assert(WQ_ITEMS >= 40, "room for the < 32 live items plus at least a few new ones");
+constexpr int WQ_ITEMS = TPL_WQ_ITEMS;   // deferred slots; a lane whose slots do not fit waits for the next round of wq_publish (never seen in practice)
+static_assert(WQ_ITEMS >= 72, "after a resolve (< 32 slots live) the 40 slots of any one lane must fit");
 struct WarpQueue {
     uint32_t env[13 * WQ_ENVS];      // [k][entry]: 10 columns, piece | cells << 8 | fl_noclear << 16, lines, env index
     uint16_t items[WQ_ITEMS];        // entry | slot << 6
@@ -318,29 +318,6 @@ struct WarpQueue {
 struct WqPos { uint32_t head, tail, ehead, etail; };      // warp-uniform, monotonically increasing (indices are taken modulo)
 
 __device__ __forceinline__ void rag_wait(bool complete);
-template <int MODE>
-__device__ __forceinline__ void wq_resolve(WarpQueue &q, WqPos &p, bool flush, const uint4 *s_tab, uint32_t *scr, uint32_t n,
-                                           uint32_t *words, uint8_t *flags, float4 *ff, int L, uint32_t one) {
-    const uint32_t lane = threadIdx.x & 31u;
-    while (p.tail - p.head >= 32u || (flush && p.tail != p.head)) {
-        if constexpr (MODE == 4) rag_wait(true);
-        const uint32_t live = p.tail - p.head, take = live < 32u ? live : 32u;
-        if (lane < take) {
-            const uint32_t item = q.items[(p.head + lane) % WQ_ITEMS], entry = item & 63u, slot = item >> 6;
-            uint32_t cols[COLS];
-#pragma unroll
-            for (int j = 0; j < COLS; ++j) cols[j] = q.env[j * WQ_ENVS + entry];
-            const uint32_t m0 = q.env[10 * WQ_ENVS + entry];
-            const PendingCtx cx{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, q.env[11 * WQ_ENVS + entry], m0 >> 16};
-            auto sink = make_resolve_sink<MODE>(q.env[12 * WQ_ENVS + entry], n, words, flags, ff, one);
-            resolve_slot(cols, cx, (int)slot, s_tab, scr, THREADS, L, sink);
-        }
-        __syncwarp();
-        p.head += take;
-        if (p.head != p.tail) p.ehead += ((q.items[p.head % WQ_ITEMS] & 63u) - p.ehead) & 63u;      // entry of the first slot left
-        else p.ehead = p.etail;
-    }
-}
 
 // Exclusive prefix sum over the warp of small counts (cnt <= 63; top = their warp maximum): one ballot per bit that is set in
 // any count -- independent instructions -- instead of the five dependent shuffle + select + add rounds of the classic scan
@@ -356,51 +333,68 @@ __device__ __forceinline__ uint32_t warp_prefix_small(uint32_t cnt, uint32_t top
     return excl;
 }
 
-// every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer); `i` = env index, or in the
-// distinct-placements form the word offset of the env's run
+// Every lane of the warp calls this once per tile (cx.mask == 0: nothing to defer); `i` = env index, or in the
+// distinct-placements form the word offset of the env's run.  Publish, then resolve while 32 slots are queued.  `flush`: resolve
+// whatever is queued (the kernels run one extra, tile-less round of their loop for that, so that the ~350 instructions of the
+// resolver exist ONCE in the kernel instead of three times -- they used to be a fifth of its code).  A lane whose slots do not
+// fit the ring waits for the next round of the loop below: after a resolve fewer than 32 slots are live, so at least
+// WQ_ITEMS - 31 >= 40 fit, i.e. any lane's.
 template <int MODE>
-__device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e, const PendingCtx &cx, uint32_t i,
+__device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e, const PendingCtx &cx, uint32_t i, bool flush,
                                            const uint4 *s_tab, uint32_t *scr, uint32_t n, uint32_t *words, uint8_t *flags,
                                            float4 *ff, int L, uint32_t one) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t cnt = (uint32_t)__popcll(cx.mask);
-    const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, cnt);
-    if (top == 0u) return;
-    const uint32_t incl = warp_prefix_small(cnt, top) + cnt;
-    const uint32_t room = WQ_ITEMS - (p.tail - p.head);
-    const bool fits = incl <= room;                                    // monotone in the lane index
-    const unsigned fit = __ballot_sync(0xFFFFFFFFu, cnt != 0u && fits);
-    if (cnt != 0u) {
-        if (fits) {
-            const uint32_t entry = (p.etail + (uint32_t)__popc(fit & ((1u << lane) - 1u))) % WQ_ENVS;
+    uint32_t cnt = (uint32_t)__popcll(cx.mask);                        // this lane's slots not yet in the queue
+    for (;;) {
+        const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, cnt);
+        if (top != 0u) {
+            const uint32_t incl = warp_prefix_small(cnt, top) + cnt;
+            const uint32_t room = WQ_ITEMS - (p.tail - p.head);
+            const bool fits = cnt != 0u && incl <= room;               // monotone in the lane index
+            const unsigned fit = __ballot_sync(0xFFFFFFFFu, fits);
+            if (fits) {
+                const uint32_t entry = (p.etail + (uint32_t)__popc(fit & ((1u << lane) - 1u))) % WQ_ENVS;
 #pragma unroll
-            for (int k = 0; k < COLS; ++k) q.env[k * WQ_ENVS + entry] = e.col[k];
-            q.env[10 * WQ_ENVS + entry] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
-            q.env[11 * WQ_ENVS + entry] = cx.lines;
-            q.env[12 * WQ_ENVS + entry] = i;
-            unsigned long long m = cx.mask;
-            uint32_t at = p.tail + incl - cnt;
-            while (m) {
-                const int sl = __ffsll((long long)m) - 1;
-                m &= m - 1ull;
-                q.items[at++ % WQ_ITEMS] = (uint16_t)(entry | ((uint32_t)sl << 6));
+                for (int k = 0; k < COLS; ++k) q.env[k * WQ_ENVS + entry] = e.col[k];
+                q.env[10 * WQ_ENVS + entry] = cx.piece | (cx.cells << 8) | (cx.fl_noclear << 16);
+                q.env[11 * WQ_ENVS + entry] = cx.lines;
+                q.env[12 * WQ_ENVS + entry] = i;
+                unsigned long long m = cx.mask;
+                uint32_t at = p.tail + incl - cnt;
+                while (m) {
+                    const int sl = __ffsll((long long)m) - 1;
+                    m &= m - 1ull;
+                    q.items[at++ % WQ_ITEMS] = (uint16_t)(entry | ((uint32_t)sl << 6));
+                }
+                cnt = 0u;
             }
-        } else {                                                       // queue full: this lane resolves its own slots now
-            auto sink = make_resolve_sink<MODE>(i, n, words, flags, ff, one);
-            unsigned long long m = cx.mask;
-            while (m) {
-                const int sl = __ffsll((long long)m) - 1;
-                m &= m - 1ull;
-                resolve_slot(e.col, cx, sl, s_tab, scr, THREADS, L, sink);
+            if (fit) {
+                p.tail += __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(fit));      // inclusive count at the last lane that fits
+                p.etail += (uint32_t)__popc(fit);
             }
+            __syncwarp();
         }
+        const bool more = top != 0u && __any_sync(0xFFFFFFFFu, cnt != 0u);      // (some lane is still waiting for room)
+        while (p.tail - p.head >= 32u || ((flush || more) && p.tail != p.head)) {
+            if constexpr (MODE == 4) rag_wait(true);
+            const uint32_t live = p.tail - p.head, take = live < 32u ? live : 32u;
+            if (lane < take) {
+                const uint32_t item = q.items[(p.head + lane) % WQ_ITEMS], entry = item & 63u, slot = item >> 6;
+                uint32_t cols[COLS];
+#pragma unroll
+                for (int j = 0; j < COLS; ++j) cols[j] = q.env[j * WQ_ENVS + entry];
+                const uint32_t m0 = q.env[10 * WQ_ENVS + entry];
+                const PendingCtx c2{0ull, m0 & 0xFFu, (m0 >> 8) & 0xFFu, q.env[11 * WQ_ENVS + entry], m0 >> 16};
+                auto sink = make_resolve_sink<MODE>(q.env[12 * WQ_ENVS + entry], n, words, flags, ff, one);
+                resolve_slot(cols, c2, (int)slot, s_tab, scr, THREADS, L, sink);
+            }
+            __syncwarp();
+            p.head += take;
+            if (p.head != p.tail) p.ehead += ((q.items[p.head % WQ_ITEMS] & 63u) - p.ehead) & 63u;      // entry of the first slot left
+            else p.ehead = p.etail;
+        }
+        if (!more) break;
     }
-    if (fit) {
-        p.tail += __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(fit));      // inclusive count at the last lane that fits
-        p.etail += (uint32_t)__popc(fit);
-    }
-    __syncwarp();
-    wq_resolve<MODE>(q, p, false, s_tab, scr, n, words, flags, ff, L, one);
 }
 
 // ---- distinct-placements form: the two warp-collective halves around the enumeration of a tile
@@ -535,34 +529,39 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
     const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
     int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
     if (t < wtiles) stage_issue(rs, st, stride, (int64_t)t * 32 + (threadIdx.x & 31), n);
-    for (; t < wtiles; t += wstep) {                                                                    // warp-uniform trip count
+    // (warp-uniform trip count; one extra round after the warp's last tile drains its queue of deferred slots: see wq_publish)
+    for (;; t += wstep) {
+        const bool drain = t >= wtiles;
         const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31);
         PendingCtx cx; cx.mask = 0ull;
         Env e;
-        stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
-        if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
-        if constexpr (RAG) {
-            uint32_t piece = 7u, cnt = 0u;
-            if (i < n) current_run(e, s_tab, piece, cnt);
-            const RagTile rt = rag_reserve(cnt, cursor);
-            rag_wait(false);
-            if (i < n) {
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
-                RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+        uint32_t at = 0u;                                // what the resolver addresses the env's slots by
+        if (!drain) {
+            stage_take(rs, e);                           // each lane reads back only what it copied itself: no warp sync needed
+            if (t + wstep < wtiles) stage_issue(rs, st, stride, i + (int64_t)wstep * 32, n);
+            if constexpr (RAG) {
+                uint32_t piece = 7u, cnt = 0u;
+                if (i < n) current_run(e, s_tab, piece, cnt);
+                const RagTile rt = rag_reserve(cnt, cursor);
+                rag_wait(false);
+                if (i < n) {
+                    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+                    RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
+                    afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+                }
+                at = rag_flush(stage, rt, words) + rt.excl;
+                if (i < n) runs[i] = (at + run_base) | (piece << 29);         // (the resolver addresses `words + at`: call-local)
+            } else {
+                if (i < n) {
+                    GlobalSink<MODE, P32> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
+                    afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+                }
+                at = (uint32_t)i;
             }
-            const uint32_t goff = rag_flush(stage, rt, words) + rt.excl;
-            if (i < n) runs[i] = (goff + run_base) | (piece << 29);       // (the resolver addresses `words + goff`: call-local)
-            wq_publish<MODE>(q, qp, e, cx, goff, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
-        } else {
-            if (i < n) {
-                GlobalSink<MODE, P32> sink{words + i, flags + i, ff + i, (uint32_t)n, one, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
-            }
-            wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
         }
+        wq_publish<MODE>(q, qp, e, cx, at, drain, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
+        if (drain) break;
     }
-    wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, flags, ff, L, one);
 }
 
 // Small batches (BASELINE configs[1]: 4096 envs = 32 CTAs on 148 SMs) are latency-bound: one warp per scheduler runs a
@@ -758,73 +757,78 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
         if (i1 < n) nep2 = episode ? episode[i1] : 0u;
         if (pool) pool_issue(pstage, pool, config_index(seed, env_base + (uint64_t)(i0 < n ? i0 : (int64_t)n - 1), nep + 1u, K));
     }
-    for (; t < wtiles; t += wstep) {                                                                    // warp-uniform trip count
+    // (warp-uniform trip count; one extra round after the warp's last tile drains its queue of deferred slots: see wq_publish)
+    for (;; t += wstep) {
+        const bool drain = t >= wtiles;
         const int64_t i = (int64_t)t * 32 + (threadIdx.x & 31), i2 = i + (int64_t)wstep * 32;
         PendingCtx cx; cx.mask = 0ull;
         Env e;
-        stage_take(rs, e);                               // each lane reads back only what it copied itself: no warp sync needed
-        const uint32_t arot = nrot, aloc = nloc, ep1 = nep + 1u, ep1_next = nep2 + 1u;
-        {
-            const int64_t i3 = i2 + (int64_t)wstep * 32;
-            if (t + wstep < wtiles) stage_issue(rs, st, stride, i2, n);
-            if (i2 < n) { nrot = rot[i2]; nloc = loc[i2]; }
-            nep = nep2;
-            if (i3 < n) nep2 = episode ? episode[i3] : 0u;
-        }
-        if (i < n) {
-            const uint32_t was = e.state;
-            int k; bool changed;
-            const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
-            if (dlines) dlines[i] = (int8_t)k;
-            if (flags) flags[i] = (uint8_t)fl;
-            if (sto) sto[i] = (int8_t)e.state;
-            acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
-            if (was == S_RUNNING && e.state != S_RUNNING) {
-                acc[0] += 1;
-                if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+        uint32_t at = 0u;                                // what the resolver addresses the env's slots by
+        if (!drain) {
+            stage_take(rs, e);                           // each lane reads back only what it copied itself: no warp sync needed
+            const uint32_t arot = nrot, aloc = nloc, ep1 = nep + 1u, ep1_next = nep2 + 1u;
+            {
+                const int64_t i3 = i2 + (int64_t)wstep * 32;
+                if (t + wstep < wtiles) stage_issue(rs, st, stride, i2, n);
+                if (i2 < n) { nrot = rot[i2]; nloc = loc[i2]; }
+                nep = nep2;
+                if (i3 < n) nep2 = episode ? episode[i3] : 0u;
             }
-            if (refill_queue(e, seed, env_base + (uint64_t)i, ep1 - 1u, gen_count)) changed = true;
-            else if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {       // TPL_RESET_DONE semantics
-                if (episode) episode[i] = ep1;
-                if (tstep) tstep[i] = 0u;                                           // a new episode: the action stream of the rollouts restarts
-                const uint32_t lane = threadIdx.x & 31u;                            // (the record landed with this tile's env records)
-                install_record(e, pstage.chunk[0][lane], pstage.chunk[1][lane], pstage.chunk[2][lane], pstage.chunk[3][lane], seed,
-                               env_base + (uint64_t)i, ep1, gen_count);
-                acc[7] += 1;
-                changed = true;
-            }
-            if (changed) {
-                st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
-                st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
-                st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
-            }
-            st[3 * stride + i] = pack_meta(e);
-        }
-        // the record the next tile's reset would install: on its way during the enumeration below
-        if (pool && t + wstep < wtiles)
-            pool_issue(pstage, pool, config_index(seed, env_base + (uint64_t)(i2 < n ? i2 : (int64_t)n - 1), ep1_next, K));
-        if constexpr (RAG) {
-            uint32_t piece = 7u, cnt = 0u;
-            if (i < n) current_run(e, s_tab, piece, cnt);
-            const RagTile rt = rag_reserve(cnt, cursor);
-            rag_wait(false);
             if (i < n) {
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
-                RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+                const uint32_t was = e.state;
+                int k; bool changed;
+                const uint32_t fl = step_env(e, s_tab, scr, THREADS, arot, aloc, L, M, k, changed);
+                if (dlines) dlines[i] = (int8_t)k;
+                if (flags) flags[i] = (uint8_t)fl;
+                if (sto) sto[i] = (int8_t)e.state;
+                acc[6] += 1; acc[4] += (uint32_t)k; acc[5] += changed ? 1u : 0u;
+                if (was == S_RUNNING && e.state != S_RUNNING) {
+                    acc[0] += 1;
+                    if (fl & F_WIN) acc[1] += 1; else if (fl & F_TOPOUT) acc[2] += 1; else acc[3] += 1;
+                }
+                if (refill_queue(e, seed, env_base + (uint64_t)i, ep1 - 1u, gen_count)) changed = true;
+                else if (pool && (e.state != S_RUNNING || e.head >= e.npieces)) {       // TPL_RESET_DONE semantics
+                    if (episode) episode[i] = ep1;
+                    if (tstep) tstep[i] = 0u;                                           // a new episode: the action stream of the rollouts restarts
+                    const uint32_t lane = threadIdx.x & 31u;                            // (the record landed with this tile's env records)
+                    install_record(e, pstage.chunk[0][lane], pstage.chunk[1][lane], pstage.chunk[2][lane], pstage.chunk[3][lane], seed,
+                                   env_base + (uint64_t)i, ep1, gen_count);
+                    acc[7] += 1;
+                    changed = true;
+                }
+                if (changed) {
+                    st[i] = make_uint4(e.col[0], e.col[1], e.col[2], e.col[3]);
+                    st[stride + i] = make_uint4(e.col[4], e.col[5], e.col[6], e.col[7]);
+                    st[2 * stride + i] = make_uint4(e.col[8], e.col[9], e.q[0], e.q[1]);
+                }
+                st[3 * stride + i] = pack_meta(e);
             }
-            const uint32_t goff = rag_flush(stage, rt, words) + rt.excl;
-            if (i < n) runs[i] = (goff + run_base) | (piece << 29);       // (the resolver addresses `words + goff`: call-local)
-            wq_publish<MODE>(q, qp, e, cx, goff, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
-        } else {
-            if (i < n) {
-                GlobalSink<MODE, P32> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
-                afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+            // the record the next tile's reset would install: on its way during the enumeration below
+            if (pool && t + wstep < wtiles)
+                pool_issue(pstage, pool, config_index(seed, env_base + (uint64_t)(i2 < n ? i2 : (int64_t)n - 1), ep1_next, K));
+            if constexpr (RAG) {
+                uint32_t piece = 7u, cnt = 0u;
+                if (i < n) current_run(e, s_tab, piece, cnt);
+                const RagTile rt = rag_reserve(cnt, cursor);
+                rag_wait(false);
+                if (i < n) {
+                    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+                    RaggedStageSink sink{sbase + rt.excl * 4u, sbase + RAG_DUMMY_WORD * 4u, 0u};
+                    afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+                }
+                at = rag_flush(stage, rt, words) + rt.excl;
+                if (i < n) runs[i] = (at + run_base) | (piece << 29);         // (the resolver addresses `words + at`: call-local)
+            } else {
+                if (i < n) {
+                    GlobalSink<MODE, P32> sink{words + i, aflags + i, ff + i, (uint32_t)n, one, nullptr};
+                    afterstates_env(e, s_tab, scr, THREADS, L, M, sink, 0, 4, &cx, one);
+                }
+                at = (uint32_t)i;
             }
-            wq_publish<MODE>(q, qp, e, cx, (uint32_t)i, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
         }
+        wq_publish<MODE>(q, qp, e, cx, at, drain, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
+        if (drain) break;
     }
-    wq_resolve<MODE>(q, qp, true, s_tab, scr, (uint32_t)n, words, aflags, ff, L, one);
     if (stats) flush_stats(acc, stats);
 }
 

@@ -1,5 +1,5 @@
-# one-off validation of the deferred-slot queue's overflow path: rebuild with a 40-entry queue, run the parity tests
-TPL_NVCC_EXTRA="-DTPL_WQ_ITEMS=40" python -c "
+# one-off validation of the deferred-slot queue's overflow path: rebuild with a 72-entry queue (the smallest allowed), run the parity tests
+TPL_NVCC_EXTRA="-DTPL_WQ_ITEMS=72" python -c "
 import importlib,sys
 sys.path.insert(0,'.')
 b=importlib.import_module('reinforcement-learning-for-playing-tetris-with-prescribed-initial-configuration-and-limited-moves_b200.build')
