@@ -231,7 +231,7 @@ struct GlobalSink {
         if constexpr (P32) {
             uint32_t lo, hi;
             asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(pcol));
-            lo += n * 4u;
+            lo = mad_fma_pipe(n * 4u, one, lo);              // (pinned to the FMA pipe: left to itself ptxas sometimes picks an ALU-pipe add)
             asm("mov.b64 %0, {%1, %2};" : "=l"(pcol) : "r"(lo), "r"(hi));
         } else {
             asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(pcol) : "r"(n * 4u), "r"(one));

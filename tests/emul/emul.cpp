@@ -38,6 +38,19 @@ struct PackedRowSink {
     void copy(int dst, int src, uint32_t extra) { row[dst] = row[src] | (extra << 3); }
 };
 
+// the kernels' compact-form sink (GlobalSink<0>): a cursor that walks along the columns of one rotation
+struct PackedCursorSink {
+    static constexpr bool PACKED = true, RAGGED = false;
+    uint32_t row[40];
+    int rot, colc;
+    void begin_rotation(int r) { rot = r; colc = 0; }
+    void put_packed_col(int, uint32_t packed) { row[rot * 10 + colc] = packed; }
+    void put_packed_col_again(int, uint32_t packed) { row[rot * 10 + colc] = packed; }
+    void next_col() { ++colc; }
+    void put_packed(int slot, uint32_t packed) { row[slot] = packed; }
+    void put(int slot, uint32_t word, uint32_t fl) { row[slot] = word | (fl << 3); }
+};
+
 // distinct-placements form: the run of one env (at most 34 words); alias rotations write to a dummy row
 struct HostRaggedSink {
     static constexpr bool PACKED = true, RAGGED = true;
@@ -100,6 +113,22 @@ int emul_afterstates_uniform(const void *state, int64_t stride, int n, uint8_t *
                 resolve_slot(e.col, cx, s, table(), scr, 1, L, sink);
             }
         }
+        for (int s = 0; s < 40; ++s) out[(size_t)s * n + i] = sink.row[s];
+    }
+    return 0;
+}
+
+// afterstates through the compact-form path of the persistent kernels (afterstates_env with a packed cursor sink), the
+// row-completing slots deferred and resolved afterwards as the kernels' queues do
+int emul_afterstates_cursor(const void *state, int64_t stride, int n, uint8_t *feats_packed, int L, int M) {
+    uint32_t *out = (uint32_t *)feats_packed;
+    for (int64_t i = 0; i < n; ++i) {
+        Env e; load_env((const uint4 *)state, stride, i, e);
+        PackedCursorSink sink; for (int s = 0; s < 40; ++s) sink.row[s] = 0xDEADBEEFu;
+        uint32_t scr[SCR_ROWS];
+        PendingCtx cx;
+        afterstates_env(e, table(), scr, 1, L, M, sink, 0, 4, &cx);
+        for (unsigned long long m = cx.mask; m; m &= m - 1ull) resolve_slot(e.col, cx, __builtin_ffsll((long long)m) - 1, table(), scr, 1, L, sink);
         for (int s = 0; s < 40; ++s) out[(size_t)s * n + i] = sink.row[s];
     }
     return 0;

@@ -47,6 +47,7 @@ class EmulEngine:
             "afterstates": [P, I64, I, P, P, P, I, I],
             "afterstates_uniform": [P, I64, I, P, I, I, I],
             "afterstates_split": [P, I64, I, P, I, I],
+            "afterstates_cursor": [P, I64, I, P, I, I],
             "gen_pieces": [P, I, I, U64, U64, P, U32],
             "step_observe": [P, I64, I, P, P, P, P, P, P, P, I, P, P, U64, U64, I, P, P, P, I, I, P, P, P],
             "rollout_random": [P, I64, I, P, I, P, P, P, I, U64, U64, I, I, I],
@@ -119,6 +120,9 @@ class EmulEngine:
             uni = np.zeros((40, s.n, 4), np.uint8)
             self.L.emul_afterstates_uniform(_np_ptr(s.planes), s.stride, s.n, _np_ptr(uni), L, M, defer)
             assert np.array_equal(uni, feats), f"warp-uniform afterstate variant (defer={defer}) differs from the plain one"
+        cur = np.full((40, s.n, 4), 0xEE, np.uint8)     # the compact-form path of the persistent kernels (cursor sink, deferred slots)
+        self.L.emul_afterstates_cursor(_np_ptr(s.planes), s.stride, s.n, _np_ptr(cur), L, M)
+        assert np.array_equal(cur, feats), "compact-form (cursor sink) afterstate variant differs from the plain one"
         spl = np.full((40, s.n, 4), 0xEE, np.uint8)     # and so must the one-thread-per-rotation variant
         self.L.emul_afterstates_split(_np_ptr(s.planes), s.stride, s.n, _np_ptr(spl), L, M)
         assert np.array_equal(spl, feats), "rotation-split afterstate variant differs from the plain one"
