@@ -740,12 +740,26 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
     WarpQueue &q = s_wq[threadIdx.x >> 5];
     RecordStage &rs = s_stage[threadIdx.x >> 5], &pstage = s_pstage[threadIdx.x >> 5];
     uint32_t *stage = s_rag + (threadIdx.x >> 5) * RAG_STAGE_WORDS;
+    const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
+    int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
+#ifndef TPL_NO_PDL_PREFETCH
+    // Hints only (no data is read): the lines of the warp's first tile are asked into L2 while the previous kernel is still
+    // finishing, so that the first loads after pdl_wait -- every warp of the grid issues them at the same moment, with nothing
+    // else to run -- find them there.  (L2 is the point of coherence: a line the previous kernel still writes stays current.)
+    if (t < wtiles) {
+        const int64_t i0 = (int64_t)t * 32 + (threadIdx.x & 31);
+        if (i0 < n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) prefetch_l2(st + j * stride + i0);
+            if ((threadIdx.x & 31) == 0) { prefetch_l2(rot + i0); prefetch_l2(loc + i0); }
+            if (episode && (threadIdx.x & 7) == 0) prefetch_l2(episode + i0);
+        }
+    }
+#endif
     pdl_wait();                                                      // nothing above reads or writes what another kernel produces
     if (RAG && cursor_clear && blockIdx.x == 0 && threadIdx.x == 0) *cursor_clear = 0u;      // the NEXT call's counter
     WqPos qp{0u, 0u, 0u, 0u};
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int wtiles = (n + 31) / 32, wstep = (int)gridDim.x * (THREADS / 32);
-    int t = (int)blockIdx.x * (THREADS / 32) + (int)(threadIdx.x >> 5);
     // The next tile's action and episode number ride in three registers, its records in shared memory (stage_issue); the episode
     // number of the tile after that rides in a fourth, because the pool record of the next tile is requested in the middle of this
     // one (pool_issue) and the number it is drawn from must have arrived by then.
