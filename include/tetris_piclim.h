@@ -9,7 +9,11 @@
  * Two groups of entry points:
  *   tpl_*        device-pointer API: every array argument is a DEVICE pointer, work is queued
  *                asynchronously on `stream` (a cudaStream_t passed as void*); the library never
- *                allocates, frees or synchronises.
+ *                allocates, frees or synchronises.  Stream order is what a caller sees; underneath, the
+ *                persistent kernels (tpl_step, tpl_afterstates*, tpl_step_observe*) are launched with
+ *                programmatic dependent launch, i.e. their set-up may overlap the tail of the previous
+ *                kernel in the stream while everything that touches data waits for it to complete
+ *                (TPL_NO_PDL=1 in the environment, read once per process, launches them plainly).
  *   tpl_env_*    host-buffer API: an opaque handle owns the device state, pinned staging and a
  *                stream; every array argument is a HOST pointer and the call returns when the
  *                outputs are valid.  This is what a ctypes binding in the reference would call

@@ -141,7 +141,7 @@ def test_compact_form_64bit_pointer_chain(gpu, golden_dir):
             "pc.case_afterstates_vs_oracle(g, 100_000, 10, 30, 5)\n"
             "pc.case_fused_step_observe(g, _pool(%r), n=50_000, steps=20)\n"
             "print('chain64-ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), golden_dir)
-    env = dict(os.environ, TPL_NO_P32="1")
+    env = dict(os.environ, TPL_NO_P32="1", TPL_NO_PDL="1")      # (and plain launches instead of programmatic dependent launch)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "chain64-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
