@@ -54,6 +54,8 @@ def expand(rows: np.ndarray, runs: np.ndarray) -> np.ndarray:
     canon = canon_of[piece].astype(np.int64)                                   # [n, 40]
     has = (piece < 7)[:, None]
     idx = np.where(has, off[:, None] + canon, 0)
+    if len(rows) == 0:                                   # no env has a piece left (every queue is empty): nothing was written
+        rows = np.zeros(1, np.uint32)
     words = np.where(has, rows[np.minimum(idx, len(rows) - 1)], np.uint32(FLAG_NOPIECE << 3))
     alias = has & (slot_of[piece[:, None], canon] != np.arange(40)[None, :])
     words = words | (alias.astype(np.uint32) * np.uint32(FLAG_ALIAS << 3))

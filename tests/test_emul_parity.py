@@ -65,3 +65,14 @@ def test_edges(emul):
 
 def test_long_episodes_queue_refill(emul):
     pc.case_long_episodes(emul)
+
+
+def test_expand_distinct_without_any_placement():
+    """distinct.expand on a batch in which no env has a piece left: `rows` is empty, every slot reads TPL_FLAG_NOPIECE
+    (found by scripts/fuzz_gpu.py with M = 1: the host helper indexed an empty array)."""
+    import importlib
+    dm = importlib.import_module("tetris_piclim").distinct if hasattr(importlib.import_module("tetris_piclim"), "distinct") \
+        else importlib.import_module("reinforcement-learning-for-playing-tetris-with-prescribed-initial-configuration-and-limited-moves_b200.distinct")
+    runs = np.full(5, np.uint32(7) << np.uint32(29), np.uint32)          # piece id 7 = no piece, offset 0
+    out = dm.expand(np.zeros(0, np.uint32), runs)
+    assert out.shape == (5, 40, 4) and (out[:, :, 0] == (16 << 3) & 0xFF).all() and not out[:, :, 1:].any()
