@@ -401,7 +401,7 @@ __device__ __forceinline__ void wq_publish(WarpQueue &q, WqPos &p, const Env &e,
 struct RagTile { uint32_t excl, total, tb; };
 // cnt = this lane's run length (0 / 9 / 17 / 34): exclusive prefix over the warp, and one atomicAdd reserving the tile's
 // words (rounded up to 4 so that every tile starts 16-byte aligned); the returned base is only needed after the enumeration
-__device__ __forceinline__ RagTile rag_reserve(uint32_t cnt, uint32_t *cursor) {
+__device__ __forceinline__ RagTile rag_reserve(uint32_t cnt, uint32_t *cursor, uint32_t one) {
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     // the run lengths are 0, 9, 17 or 34: the prefix is three ballots (independent) instead of a five-round shuffle scan
     const unsigned b9 = __ballot_sync(0xFFFFFFFFu, cnt == 9u), b17 = __ballot_sync(0xFFFFFFFFu, cnt == 17u), b34 = __ballot_sync(0xFFFFFFFFu, cnt == 34u);
@@ -409,7 +409,11 @@ __device__ __forceinline__ RagTile rag_reserve(uint32_t cnt, uint32_t *cursor) {
     t.excl = 9u * (uint32_t)__popc(b9 & lt) + 17u * (uint32_t)__popc(b17 & lt) + 34u * (uint32_t)__popc(b34 & lt);
     t.total = 9u * (uint32_t)__popc(b9) + 17u * (uint32_t)__popc(b17) + 34u * (uint32_t)__popc(b34);
     t.tb = 0u;
-    if (lane == 0u && t.total) t.tb = atomicAdd(cursor, (t.total + 3u) & ~3u);
+    // The address is made to LOOK thread-dependent ((one - 1) * threadIdx.x = 0; `one` is the opaque kernel parameter 1): on a provably
+    // warp-uniform address ptxas wraps the atomic -- also an inline-PTX one -- in its warp-aggregation pattern, whose result
+    // broadcast (a shuffle right behind the atomic) made every tile wait for the contended counter HERE, 7 % of the
+    // distinct-form step's warp time, instead of after the enumeration, where the base is first needed.
+    if (lane == 0u && t.total) t.tb = atomicAdd(cursor + (one - 1u) * threadIdx.x, (t.total + 3u) & ~3u);
     return t;
 }
 // staging area -> rows[tile base ...] with 16-byte stores; returns the tile base (word offset).  The trailing __syncwarp orders
@@ -542,7 +546,7 @@ afterstates_kernel(const uint4 *__restrict__ st, int64_t stride, int n, uint32_t
             if constexpr (RAG) {
                 uint32_t piece = 7u, cnt = 0u;
                 if (i < n) current_run(e, s_tab, piece, cnt);
-                const RagTile rt = rag_reserve(cnt, cursor);
+                const RagTile rt = rag_reserve(cnt, cursor, one);
                 rag_wait(false);
                 if (i < n) {
                     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
@@ -823,7 +827,7 @@ step_observe_kernel(uint4 *st, int64_t stride, int n, const uint8_t *__restrict_
             if constexpr (RAG) {
                 uint32_t piece = 7u, cnt = 0u;
                 if (i < n) current_run(e, s_tab, piece, cnt);
-                const RagTile rt = rag_reserve(cnt, cursor);
+                const RagTile rt = rag_reserve(cnt, cursor, one);
                 rag_wait(false);
                 if (i < n) {
                     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
