@@ -428,14 +428,16 @@ __device__ __forceinline__ int greedy_value(int w0, int w1, int w2, int w3, int 
     return v;
 }
 
-template <bool W16>
+// INORDER: every put comes with a higher slot number than the one before (the enumeration's own order, when the deferred slots
+// are resolved elsewhere): "first strictly greater wins" then IS the lowest-slot tie-break, one compare less per slot.
+template <bool W16, bool INORDER = false>
 struct GreedySinkT {
     static constexpr bool PACKED = false, RAGGED = false;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
         const int v = greedy_value<W16>(w0, w1, w2, w3, w4, w5, word, fl);
-        if (v > best || (v == best && slot < best_slot)) { best = v; best_slot = slot; }
+        if (INORDER ? v > best : (v > best || (v == best && slot < best_slot))) { best = v; best_slot = slot; }
     }
 };
 

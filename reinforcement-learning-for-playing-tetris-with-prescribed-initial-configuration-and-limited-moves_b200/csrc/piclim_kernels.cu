@@ -922,7 +922,7 @@ __device__ __forceinline__ void rollout_greedy_step_pooled(Env &e, uint32_t &ep,
         ep += 1; t = 0; acc[7] += 1;
         install_config(e, pool, config_index(seed, env, ep, K), seed, env, ep, gen_count);
     }
-    GreedySinkT<W16> sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};
+    GreedySinkT<W16, true> sink{gw.w[0], gw.w[1], gw.w[2], gw.w[3], gw.w[4], gw.w[5], (int)0x80000000, 40};   // (deferred slots: pooled below)
     PendingCtx cx; cx.mask = 0ull;
     if (valid) afterstates_env(e, tab, scr, THREADS, L, M, sink, 0, 4, &cx);
     const uint32_t cnt = (uint32_t)__popcll(cx.mask);
