@@ -1,5 +1,5 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_step_observe or rollout_greedy or library_loaded or ragged or edges or long_episodes or deterministic" > gpurun_out/r2b6_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2b6_pytest.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused_step_observe or rollout_greedy or library_loaded or ragged or edges or long_episodes or deterministic" > gpurun_out/r2b_check_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2b_check_pytest.log
 python scripts/prof.py --what fused --steps 40 2>&1 | tail -1
 python scripts/prof.py --what fused --steps 40 2>&1 | tail -1
 python scripts/prof.py --what fused_distinct --steps 40 2>&1 | tail -1
