@@ -6,6 +6,11 @@
 
 namespace tpl {
 
+// Sinks that only want the VALUE of a placement (the greedy rollout's arg-max) declare `static constexpr bool VALUE_ONLY = true`
+// and take the fast path's words through begin_env / put_value (see GreedySinkT): no flags word, no alias copies.
+template <class S, class = void> struct SinkValueOnly { static constexpr bool value = false; };
+template <class S> struct SinkValueOnly<S, decltype((void)S::VALUE_ONLY)> { static constexpr bool value = S::VALUE_ONLY; };
+
 // ---------------------------------------------------------------------------------------------
 // boundary conversions: 20 x u16 bitrows (row 0 = top, bit c = column c) <-> 10 bit-columns
 // ---------------------------------------------------------------------------------------------
@@ -126,6 +131,7 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
     // No lane of this warp fits a shape at column C: only the clamp alias.  Without piece-sorted warps (UNIFORM) that is known
     // statically for column 9 of rotations 0 and 2, where the narrowest shape of any piece is two wide (cmax_warp = 8).
     if (UNIFORM ? (C > 6 && C > cmax_warp) : (C == 9 && cmax_warp < 9)) {
+        if constexpr (SinkValueOnly<Sink>::value) return;         // (an alias: same value as the slot it repeats, higher number)
         if constexpr (Sink::PACKED) { word |= F_ALIAS << 3; if (!pend) sink.put_packed_col(C, word); }
         else { fl |= F_ALIAS; if (!pend) sink.put(r * 10 + C, word, fl); }
         if (pend) nsmask |= 1u << C;
@@ -198,6 +204,13 @@ __device__ __forceinline__ void slot_fast(Sink &sink, int r, const int (&H)[14],
             if (!pend) sink.put_packed_col(C, word); else nsmask |= 1u << C;
         }
         sink.next_col();
+    } else if constexpr (SinkValueOnly<Sink>::value) {
+        // value only: a column the shape does not fit repeats an earlier slot (same value, higher number: it can never win the
+        // lowest-slot tie-break), so it is simply not offered; nothing is carried from column to column
+        const bool fits = C <= 6 || C + w <= COLS;
+        const bool pnew = !top && full != 0u;
+        if (fits && pnew) pmask = mad_fma_pipe(one, 1u << C, pmask);
+        if (fits && !pnew) sink.put_value(r * 10 + C, wnew, top);
     } else {
         const bool pnew = !top && full != 0u;
         wnew = top ? U : wnew;
@@ -320,6 +333,7 @@ __device__ __forceinline__ void afterstates_env_impl(const Env &e, const uint4 *
     const uint32_t K = 0u - ((cells + 4u) << 8);                             // holes' = agg' - (cells + 4)
     const uint32_t fl_noclear = ((int)e.moves + 1 >= M) ? F_LOSE : 0u;       // :389-391
     unsigned long long pending = 0ull, notstored = 0ull;
+    if constexpr (SinkValueOnly<Sink>::value) sink.begin_env(U, fl_noclear);
 
 #ifndef TPL_ROT_UNROLL
 #define TPL_ROT_UNROLL 1            // tuning knob: unrolling the rotation loop was measured and does not pay
@@ -430,14 +444,29 @@ __device__ __forceinline__ int greedy_value(int w0, int w1, int w2, int w3, int 
 
 // INORDER: every put comes with a higher slot number than the one before (the enumeration's own order, when the deferred slots
 // are resolved elsewhere): "first strictly greater wins" then IS the lowest-slot tie-break, one compare less per slot.
+// ... and the fast path then hands over values only (VALUE_ONLY): without a completed row a placement cannot win, so its flags are
+// either those of a top-out -- value of the unchanged board + w5, one constant per env (vU) -- or the env's no-clear flags (nothing
+// or LOSE: the constant bN, which rides as the accumulator of the dot products): two dot products and one select per slot.
 template <bool W16, bool INORDER = false>
 struct GreedySinkT {
-    static constexpr bool PACKED = false, RAGGED = false;
+    static constexpr bool PACKED = false, RAGGED = false, VALUE_ONLY = INORDER;
     int w0, w1, w2, w3, w4, w5;
     int best, best_slot;
+    int vU = 0, bN = 0;
     __device__ __forceinline__ void put(int slot, uint32_t word, uint32_t fl) {
         const int v = greedy_value<W16>(w0, w1, w2, w3, w4, w5, word, fl);
         if (INORDER ? v > best : (v > best || (v == best && slot < best_slot))) { best = v; best_slot = slot; }
+    }
+    __device__ __forceinline__ void begin_env(uint32_t U, uint32_t fl_noclear) {
+        vU = greedy_value<W16>(w0, w1, w2, w3, w4, w5, U, F_TOPOUT);
+        bN = (fl_noclear & (F_LOSE | F_TOPOUT)) ? w5 : 0;
+    }
+    __device__ __forceinline__ void put_value(int slot, uint32_t wnew, bool top) {
+        int v;
+        if constexpr (W16) v = dp2a_hi((uint32_t)w2 & 0xFFFFu | ((uint32_t)w3 << 16), wnew, dp2a_lo((uint32_t)w0 & 0xFFFFu | ((uint32_t)w1 << 16), wnew, bN));
+        else v = greedy_value<false>(w0, w1, w2, w3, w4, w5, wnew, 0u) + bN;
+        v = top ? vU : v;
+        if (v > best) { best = v; best_slot = slot; }
     }
 };
 
